@@ -1,0 +1,477 @@
+// at_kernels.cuh -- sm_100a device code of the alignTools DP core.
+//
+// K1  at_fill_affine<MODE,R,JUMP>  : Gotoh M/L/U(/J) fill, one pair per warp, int32 lanes.
+//     at_fill_linear<MODE,R>       : single-plane fill (overlap max-plus / edit min-plus).
+// K3  at_traceback<...>            : device traceback, one thread per pair, two walks
+//                                    (count, then emit CIGAR runs + gapped strings).
+//
+// Geometry.  Rows i <-> read s1, columns j <-> target s2.  A warp
+// sweeps a STRIPE of 32*R rows over all columns as a systolic array: lane k owns rows
+// row0+k*R .. +R-1 and at step t works on column j = t - k, so the 32 lanes sit on one
+// anti-diagonal of R-row blocks.  The last row of each lane (M+o, L, H=max(L,M,U[,J]) and
+// the 2-bit argmax code of H) moves to lane k+1 with __shfl_up_sync once per step; lane 31
+// parks it in a boundary row that lane 0 reads back on the next stripe (reads longer than
+// 32*R rows).  Per-row state (M+o, U, H, code, J of column j-1) stays in registers.
+//
+// Traceback pointers: one nibble per cell, bits 0-1 = pointerM (0 LOW, 1 MID, 2 UPP,
+// 3 HOME|JUMP), bit 2 = pointerL is MID (gap opened), bit 3 = pointerU is UPP (gap
+// extended); fit+jump adds a 1-bit plane (pointerJ is JUMP).  Reference planes:
+// src/alignment.h:44-47, values :27-34.  Nibbles of 8 consecutive steps of one row are
+// packed into a 32-bit word (earliest step in the top nibble) and stored as
+//   word[((stripe*G + step/8)*R + r)*32 + lane]           (128-byte coalesced rows)
+// i.e. in SKEWED coordinates (step = column + lane), so every store is a full line.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace at {
+
+enum { MODE_GLOBAL = 0, MODE_LOCAL = 1, MODE_FIT = 2, MODE_OVERLAP = 3, MODE_EDIT = 4 };
+enum { ST_LOW = 0, ST_MID = 1, ST_UPP = 2, ST_JUMP = 3 };   // also the 2-bit pointerM codes
+enum { CIG_M = 0, CIG_I = 1, CIG_D = 2, CIG_N = 3 };
+
+// -INFINITY stand-in: a NEG-like value never beats a finite one as long
+// as (l1+l2+2)*max|param| < 2^27, which the host checks (AT_E_RANGE).
+#define AT_NEG (-(1 << 29))
+#define AT_NEG_INIT (-(1 << 30) - (1 << 29))
+
+struct FillArgs {
+	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
+	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
+	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
+	const uint32_t *jobs;    // pair indices handled by this launch (largest first)
+	uint32_t        n_jobs;
+	uint32_t       *counter; // dynamic job queue
+	uint32_t       *ptr;     // traceback pointer arena (32-bit words)
+	const uint64_t *ptr_off; // [pair] word offset of the pair's pointer block (chunk-local index)
+	uint32_t        pair_base; // first pair of the chunk (ptr_off is indexed pair - pair_base)
+	int4           *bnd;     // stripe boundary rows, one slab per resident warp
+	uint32_t        bnd_stride;
+	int32_t        *score;   uint32_t *end_i;  uint32_t *end_j;  uint8_t *end_state;
+	int             m, u, o, e, jp;
+	int             want_ptr;
+};
+
+__device__ __forceinline__ uint32_t steps_last(uint32_t l2, int align_mask) { return (l2 + 31u) | (uint32_t)align_mask; }
+
+// ------------------------------------------------------------------------------------
+// Affine fill.  Per cell (reference recurrences src/alignment.h:451-462 global, :635-667
+// fit, :825-841 local; tie rules SURVEY.md A.0):
+//   M = max5(L'+s, M'+s, U'+s, X)   first strictly greater wins, order L,M,U,(J|HOME)
+//   L = max(L^+e, M^+o)             extend wins ties     (^ = cell above)
+//   U = max(M<+o, U<+e)             open wins ties       (< = cell to the left)
+//   J = max(M<+j, J<)  or  J<       enter wins ties; entering forbidden on listed columns
+// H = max(L,M,U[,J]) and its argmax code are produced where the cell is computed and
+// consumed by the diagonal neighbour, so pointerM(i,j) == code(i-1,j-1) unless HOME wins.
+// ------------------------------------------------------------------------------------
+template <int MODE, int R, bool JUMP>
+__device__ __forceinline__ void fill_affine_pair(const FillArgs &a, const uint32_t p, const int lane, const uint32_t warp_slot)
+{
+	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
+	const uint8_t *__restrict__ q  = a.q + a.q_off[p];
+	const uint8_t *__restrict__ tg = a.t + a.t_off[p];
+	const uint8_t *__restrict__ jm = JUMP ? a.jmask + a.t_off[p] : nullptr;
+	uint32_t *__restrict__ ptr = a.ptr + a.ptr_off[p - a.pair_base];
+	const int m = a.m, u = a.u, o = a.o, e = a.e, jpo = a.jp - a.o;
+	constexpr int RPP = 32 * R;                       // rows per stripe
+	const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
+	const uint32_t t_last = steps_last(l2, JUMP ? 31 : 7);
+	const uint32_t G = (t_last >> 3) + 1, GJ = (t_last >> 5) + 1;
+	uint32_t *__restrict__ ptrJ = ptr + (size_t)n_stripes * G * RPP;   // J bit-plane follows the nibble plane
+	int4 *__restrict__ bnd = a.bnd + (size_t)warp_slot * a.bnd_stride;
+	const bool want_ptr = a.want_ptr != 0;
+
+	int lbest = AT_NEG_INIT, lbi = 0, lbj = 0;                 // local: first maximum in row-major order
+	int capM = AT_NEG_INIT, capMj = 0, capL = AT_NEG_INIT, capLj = 0;   // fit: last-row search
+	int gH = 0, gC = 0;                                       // global: cell (l1,l2)
+
+	for (uint32_t stripe = 0; stripe < n_stripes; ++stripe) {
+		const uint32_t row0 = stripe * RPP + lane * R;        // matrix row above the lane's strip
+		const bool last_stripe = stripe + 1 == n_stripes;
+		int ac[R], Mol[R], Ul[R], Hl[R], Cl[R], Jl[R], best[R], bj[R];
+		uint32_t acc[R], accJ[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const uint32_t ri = row0 + r;                     // 0-based read index; matrix row i = ri+1
+			ac[r] = ri < l1 ? (int)q[ri] : 0x100;
+			const int i = (int)ri + 1;
+			if (MODE == MODE_GLOBAL)      { Mol[r] = AT_NEG; Ul[r] = AT_NEG; Hl[r] = o + e * i; Cl[r] = ST_LOW; }   // :432-436
+			else if (MODE == MODE_LOCAL)  { Mol[r] = o;      Ul[r] = 0;      Hl[r] = 0;         Cl[r] = ST_LOW; }   // calloc zeros
+			else                          { Mol[r] = AT_NEG; Ul[r] = AT_NEG; Hl[r] = AT_NEG;    Cl[r] = ST_MID; }   // :612-617
+			Jl[r] = AT_NEG; acc[r] = 0; accJ[r] = 0;
+			best[r] = ri < l1 ? AT_NEG_INIT : 0x7fffffff; bj[r] = 0;
+		}
+		// what this lane hands to lane+1 before it becomes active: column 0 of its last row
+		int sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
+		int sL = MODE == MODE_GLOBAL ? o + e * (int)(row0 + R) : (MODE == MODE_LOCAL ? 0 : AT_NEG);
+		// diagonal input of the first row at column 1: H(row0, 0)
+		int pH, pC;
+		if (row0 == 0) {
+			if (MODE == MODE_GLOBAL)     { pH = o < 0 ? 0 : o; pC = o < 0 ? ST_MID : ST_LOW; }   // max5(L=o, M=0, U=o)
+			else if (MODE == MODE_LOCAL) { pH = 0; pC = ST_LOW; }
+			else                         { pH = 0; pC = ST_MID; }                                // M[0][0]=U[0][0]=0, L=-inf
+		} else {
+			if (MODE == MODE_GLOBAL)     { pH = o + e * (int)row0; pC = ST_LOW; }
+			else if (MODE == MODE_LOCAL) { pH = 0; pC = ST_LOW; }
+			else                         { pH = AT_NEG; pC = ST_MID; }
+		}
+		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
+		int4 top_next = make_int4(0, 0, 0, 0);
+		if (stripe > 0 && lane == 0) top_next = bnd[1];
+
+		for (uint32_t t = 1; t <= t_last; ++t) {
+			const int j = (int)t - lane;
+			int rM = __shfl_up_sync(0xffffffffu, sM, 1);
+			int rL = __shfl_up_sync(0xffffffffu, sL, 1);
+			int rH = __shfl_up_sync(0xffffffffu, sH, 1);
+			int rC = __shfl_up_sync(0xffffffffu, sC, 1);
+			if (lane == 0) {
+				if (stripe == 0) {    // matrix row 0 at column j = t
+					if (MODE == MODE_GLOBAL)     { rM = AT_NEG; rL = AT_NEG; rH = o + e * j; rC = ST_UPP; }   // :437-441
+					else if (MODE == MODE_LOCAL) { rM = o;      rL = 0;      rH = 0;         rC = ST_LOW; }
+					else                         { rM = o;      rL = AT_NEG; rH = 0;         rC = ST_MID; }   // :619-624
+				} else {
+					rM = top_next.x; rL = top_next.y; rH = top_next.z; rC = top_next.w;
+					if (t + 1 <= l2) top_next = bnd[t + 1];
+				}
+			}
+			int D = pH, DC = pC;
+			pH = rH; pC = rC;
+			if (j >= 1 && j <= (int)l2) {
+				const int c = (int)__ldg(tg + (j - 1));
+				bool allowed = false;
+				if (JUMP) allowed = __ldg(jm + (j - 1)) == 0;
+				int Lup = rL, MoUp = rM;
+				int Mo = 0, Ln = 0, H = 0, code = 0;
+#pragma unroll
+				for (int r = 0; r < R; ++r) {
+					const int s = (ac[r] == c) ? m : u;
+					const int Mraw = D + s;
+					int pm = DC, Mn = Mraw;
+					if (MODE == MODE_LOCAL) { if (Mraw < 0) pm = 3; Mn = max(Mraw, 0); }    // HOME: 0.0 strictly greater (:825)
+					const int Lext = Lup + e;
+					const bool fL = MoUp > Lext;            // gap opened (MID) only when strictly better (:456)
+					Ln = max(Lext, MoUp);
+					const int Uext = Ul[r] + e;
+					const bool fU = Uext > Mol[r];          // gap extended (UPP) only when strictly better (:460)
+					const int Un = max(Uext, Mol[r]);
+					int Jn = AT_NEG; bool fJ = false;
+					if (JUMP) {
+						const int ent = allowed ? Mol[r] + jpo : AT_NEG;    // M[i][j-1] + jump (:660)
+						fJ = Jl[r] > ent;                   // stay in J only when strictly better
+						Jn = max(ent, Jl[r]);
+					}
+					Mo = Mn + o;
+					const int t1 = max(Ln, Mn);
+					H = max(t1, Un);
+					code = (H != Ln) + (H != t1);           // 0 LOW, 1 MID, 2 UPP: first strictly greater in order L,M,U
+					if (JUMP) { if (Jn > H) code = ST_JUMP; H = max(H, Jn); }
+					const uint32_t nib = (uint32_t)pm | (fL ? 4u : 0u) | (fU ? 8u : 0u);
+					acc[r] = (acc[r] << 4) | nib;
+					if (JUMP) accJ[r] = (accJ[r] << 1) | (fJ ? 1u : 0u);
+					if (MODE == MODE_LOCAL) { if (Mn > best[r]) { best[r] = Mn; bj[r] = j; } }   // :830-833
+					if (MODE == MODE_FIT) {
+						if (r == cap_r && j < (int)l2) {     // column l2 excluded (:677, :684)
+							if (Mn > capM) { capM = Mn; capMj = j; }
+							if (Ln > capL) { capL = Ln; capLj = j; }
+						}
+					}
+					if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) { gH = H; gC = code; } }
+					// roll the per-row state
+					D = Hl[r]; DC = Cl[r];
+					Hl[r] = H; Cl[r] = code; Ul[r] = Un; Mol[r] = Mo; if (JUMP) Jl[r] = Jn;
+					Lup = Ln; MoUp = Mo;
+				}
+				sM = Mo; sL = Ln; sH = H; sC = code;
+				if (lane == 31 && !last_stripe) bnd[j] = make_int4(sM, sL, sH, sC);
+			} else {
+#pragma unroll
+				for (int r = 0; r < R; ++r) { acc[r] <<= 4; if (JUMP) accJ[r] <<= 1; }
+			}
+			if ((t & 7u) == 7u && want_ptr) {
+				uint32_t *w = ptr + ((size_t)(stripe * G + (t >> 3)) * R) * 32 + lane;
+#pragma unroll
+				for (int r = 0; r < R; ++r) w[r * 32] = acc[r];
+			}
+			if (JUMP && (t & 31u) == 31u && want_ptr) {
+				uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (t >> 5)) * R) * 32 + lane;
+#pragma unroll
+				for (int r = 0; r < R; ++r) w[r * 32] = accJ[r];
+			}
+		}
+		if (MODE == MODE_LOCAL) {
+#pragma unroll
+			for (int r = 0; r < R; ++r)
+				if (best[r] != 0x7fffffff && best[r] > lbest) { lbest = best[r]; lbi = (int)(row0 + r) + 1; lbj = bj[r]; }
+		}
+		__syncwarp();
+	}
+
+	// ---- end cell (reference: :466-469 global, :673-690 fit, running max :830-833 local) ----
+	if (MODE == MODE_LOCAL) {
+#pragma unroll
+		for (int d = 16; d >= 1; d >>= 1) {
+			const int ov = __shfl_xor_sync(0xffffffffu, lbest, d);
+			const int oi = __shfl_xor_sync(0xffffffffu, lbi, d);
+			const int oj = __shfl_xor_sync(0xffffffffu, lbj, d);
+			if (ov > lbest || (ov == lbest && oi < lbi)) { lbest = ov; lbi = oi; lbj = oj; }
+		}
+		if (lane == 0) { a.score[p] = lbest; a.end_i[p] = lbi; a.end_j[p] = lbj; a.end_state[p] = ST_MID; }
+	} else {
+		const int owner = (int)(((l1 - 1) % RPP) / R);
+		if (lane == owner) {
+			if (MODE == MODE_GLOBAL) { a.score[p] = gH; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = (uint8_t)gC; }
+			else {
+				const bool useL = capL > capM;            // L replaces M only when strictly greater (:685)
+				a.score[p] = useL ? capL : capM; a.end_i[p] = l1; a.end_j[p] = useL ? capLj : capMj;
+				a.end_state[p] = useL ? ST_LOW : ST_MID;
+			}
+		}
+	}
+}
+
+template <int MODE, int R, bool JUMP>
+__global__ void __launch_bounds__(128) at_fill_affine(const FillArgs a)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0) job = atomicAdd(a.counter, 1u);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= a.n_jobs) break;
+		fill_affine_pair<MODE, R, JUMP>(a, a.jobs[job], lane, warp_slot);
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Single-plane fill: overlap (src/alignment.h:926-964, linear gap `o`, order
+// LEFT > DIAGONAL > RIGHT, 2-bit pointers, 16 steps per word) and edit distance
+// (:291-315, min-plus, unit gaps, no pointers).
+// ------------------------------------------------------------------------------------
+template <int MODE, int R>
+__device__ __forceinline__ void fill_linear_pair(const FillArgs &a, const uint32_t p, const int lane, const uint32_t warp_slot)
+{
+	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
+	const uint8_t *__restrict__ q  = a.q + a.q_off[p];
+	const uint8_t *__restrict__ tg = a.t + a.t_off[p];
+	uint32_t *__restrict__ ptr = MODE == MODE_OVERLAP ? a.ptr + a.ptr_off[p - a.pair_base] : nullptr;
+	const int m = a.m, u = a.u, o = a.o;
+	constexpr int RPP = 32 * R;
+	const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
+	const uint32_t t_last = steps_last(l2, 15);
+	const uint32_t G = (t_last >> 4) + 1;
+	int4 *__restrict__ bnd = a.bnd + (size_t)warp_slot * a.bnd_stride;
+	const bool want_ptr = a.want_ptr != 0 && MODE == MODE_OVERLAP;
+	int capM = 0, capMj = 0;     // overlap: M[l1][0] = 0 seeds the search (:954-959)
+	int eH = 0;                  // edit: M[l1][l2]
+
+	for (uint32_t stripe = 0; stripe < n_stripes; ++stripe) {
+		const uint32_t row0 = stripe * RPP + lane * R;
+		const bool last_stripe = stripe + 1 == n_stripes;
+		int ac[R], Ml[R];
+		uint32_t acc[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const uint32_t ri = row0 + r;
+			ac[r] = ri < l1 ? (int)q[ri] : 0x100;
+			Ml[r] = MODE == MODE_OVERLAP ? 0 : (int)ri + 1;     // M[i][0] = 0 (:938) | i (:301)
+			acc[r] = 0;
+		}
+		int sM = Ml[R - 1];
+		int pH = MODE == MODE_OVERLAP ? 0 : (int)row0;           // M[row0][0]
+		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
+		int top_next = 0;
+		if (stripe > 0 && lane == 0) top_next = bnd[1].x;
+
+		for (uint32_t t = 1; t <= t_last; ++t) {
+			const int j = (int)t - lane;
+			int rM = __shfl_up_sync(0xffffffffu, sM, 1);
+			if (lane == 0) {
+				if (stripe == 0) rM = MODE == MODE_OVERLAP ? AT_NEG : j;      // M[0][j] = -inf (:937) | j (:302)
+				else { rM = top_next; if (t + 1 <= l2) top_next = bnd[t + 1].x; }
+			}
+			int D = pH;
+			pH = rM;
+			if (j >= 1 && j <= (int)l2) {
+				const int c = (int)__ldg(tg + (j - 1));
+				int Mup = rM, v = 0;
+#pragma unroll
+				for (int r = 0; r < R; ++r) {
+					const bool eq = ac[r] == c;
+					if (MODE == MODE_OVERLAP) {
+						const int left = Ml[r] + o, diag = D + (eq ? m : u), up = Mup + o;
+						v = left; uint32_t code = 1;                       // 1 LEFT, 2 DIAGONAL, 3 RIGHT (0 = never set)
+						if (diag > v) { v = diag; code = 2; }
+						if (up > v)   { v = up;   code = 3; }
+						acc[r] = (acc[r] << 2) | code;
+						if (r == cap_r && j < (int)l2) { if (v > capM) { capM = v; capMj = j; } }
+					} else {
+						const int left = Ml[r] + 1, diag = D + (eq ? 0 : u), up = Mup + 1;
+						v = min(min(left, diag), up);                     // min3 (:280-286)
+						if (r == cap_r && j == (int)l2) eH = v;
+					}
+					D = Ml[r]; Ml[r] = v; Mup = v;
+				}
+				sM = v;
+				if (lane == 31 && !last_stripe) bnd[j].x = sM;
+			} else if (MODE == MODE_OVERLAP) {
+#pragma unroll
+				for (int r = 0; r < R; ++r) acc[r] <<= 2;
+			}
+			if (want_ptr && (t & 15u) == 15u) {
+				uint32_t *w = ptr + ((size_t)(stripe * G + (t >> 4)) * R) * 32 + lane;
+#pragma unroll
+				for (int r = 0; r < R; ++r) w[r * 32] = acc[r];
+			}
+		}
+		__syncwarp();
+	}
+	const int owner = (int)(((l1 - 1) % RPP) / R);
+	if (lane == owner) {
+		if (MODE == MODE_OVERLAP) { a.score[p] = capM; a.end_i[p] = l1; a.end_j[p] = capMj; a.end_state[p] = ST_MID; }
+		else { a.score[p] = eH; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = ST_MID; }
+	}
+}
+
+template <int MODE, int R>
+__global__ void __launch_bounds__(128) at_fill_linear(const FillArgs a)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0) job = atomicAdd(a.counter, 1u);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= a.n_jobs) break;
+		fill_linear_pair<MODE, R>(a, a.jobs[job], lane, warp_slot);
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// K3 traceback (reference: trace_back_gla :372-412, trace_back_fit_affine_jump :558-592,
+// trace_back_local_affine :766-800, trace_back_overlap :896-922).  The pointer is read at
+// the cell BEFORE the move; local emits the HOME cell's column; global flushes the
+// remaining target then read symbols after the loop.
+// ------------------------------------------------------------------------------------
+struct TraceArgs {
+	const uint8_t  *q;  const uint64_t *q_off;  const uint32_t *q_len;
+	const uint8_t  *t;  const uint64_t *t_off;  const uint32_t *t_len;
+	const uint32_t *ptr; const uint64_t *ptr_off;
+	const uint8_t  *rclass;    // [pair] rows-per-lane R the fill used for the pair
+	uint32_t        pair_base, n_pairs;   // chunk
+	const uint32_t *end_i, *end_j; const uint8_t *end_state;
+	uint32_t       *beg_i, *beg_j;
+	uint32_t       *n_ops, *n_cols;       // [pair] written by the count walk
+	const uint64_t *ops_off, *cols_off;   // [n_chunk+1] exclusive scans (chunk-local index)
+	uint32_t       *cigar;                // dense ops of the chunk
+	uint8_t        *aln1, *aln2;          // dense columns of the chunk
+	int             mode, jump, emit;
+};
+
+struct PtrView {
+	const uint32_t *ptr, *ptrJ;
+	uint32_t R, RPP, G, GJ;
+	__device__ __forceinline__ uint32_t nib(uint32_t i, uint32_t j) const {
+		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
+		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 3)) * R + r) * 32 + lane);
+		return (w >> (4 * (7 - (t & 7)))) & 15u;
+	}
+	__device__ __forceinline__ uint32_t jbit(uint32_t i, uint32_t j) const {
+		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
+		const uint32_t w = __ldg(ptrJ + ((size_t)(stripe * GJ + (t >> 5)) * R + r) * 32 + lane);
+		return (w >> (31 - (t & 31))) & 1u;
+	}
+	__device__ __forceinline__ uint32_t two(uint32_t i, uint32_t j) const {   // overlap: 2 bits, 16 steps per word
+		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
+		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 4)) * R + r) * 32 + lane);
+		return (w >> (2 * (15 - (t & 15)))) & 3u;
+	}
+};
+
+struct Emitter {
+	uint32_t *cig; uint8_t *a1, *a2; bool emit;
+	uint32_t n_ops, n_cols, run, op; uint32_t tot_ops, tot_cols;
+	__device__ __forceinline__ void flush_run() {
+		if (run) { if (cig) cig[tot_ops - 1 - n_ops] = (run << 4) | op; ++n_ops; }
+	}
+	__device__ __forceinline__ void col(uint32_t o, uint8_t x, uint8_t y) {
+		if (run && o != op) { flush_run(); run = 0; }
+		op = o; ++run;
+		if (a1) { a1[tot_cols - 1 - n_cols] = x; a2[tot_cols - 1 - n_cols] = y; }
+		++n_cols;
+	}
+};
+
+__global__ void __launch_bounds__(128) at_traceback(const TraceArgs a)
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= a.n_pairs) return;
+	const uint32_t p = a.pair_base + k;
+	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
+	const uint8_t *q = a.q + a.q_off[p], *tg = a.t + a.t_off[p];
+	PtrView pv;
+	pv.R = a.rclass[p]; pv.RPP = 32 * pv.R;
+	const uint32_t n_stripes = (l1 + pv.RPP - 1) / pv.RPP;
+	const bool jump = a.jump != 0;
+	if (a.mode == MODE_OVERLAP) { const uint32_t tl = steps_last(l2, 15); pv.G = (tl >> 4) + 1; pv.GJ = 0; }
+	else { const uint32_t tl = steps_last(l2, jump ? 31 : 7); pv.G = (tl >> 3) + 1; pv.GJ = (tl >> 5) + 1; }
+	pv.ptr = a.ptr + a.ptr_off[k];
+	pv.ptrJ = pv.ptr + (size_t)n_stripes * pv.G * pv.RPP;
+	Emitter em;
+	em.emit = a.emit != 0; em.n_ops = em.n_cols = em.run = 0; em.op = 0;
+	em.tot_ops = em.emit ? a.n_ops[p] : 0; em.tot_cols = em.emit ? a.n_cols[p] : 0;
+	em.cig = em.emit && a.cigar ? a.cigar + a.ops_off[k] : nullptr;
+	em.a1 = em.emit && a.aln1 ? a.aln1 + a.cols_off[k] : nullptr;
+	em.a2 = em.emit && a.aln2 ? a.aln2 + a.cols_off[k] : nullptr;
+	uint32_t i = a.end_i[p], j = a.end_j[p], state = a.end_state[p];
+
+	if (a.mode == MODE_OVERLAP) {
+		while (j > 0) {                                   // :899
+			const uint32_t c = pv.two(i, j);
+			if (c == 1)      { --j; em.col(CIG_D, '-', tg[j]); }               // LEFT
+			else if (c == 2) { --i; --j; em.col(CIG_M, q[i], tg[j]); }         // DIAGONAL
+			else if (c == 3) { --i; em.col(CIG_I, q[i], '-'); }                // RIGHT
+			else break;                                   // unset pointer: unreachable on a finite path
+		}
+	} else {
+		bool home = false;
+		for (;;) {
+			const bool go = a.mode == MODE_FIT ? (i > 0) : (i > 0 && j > 0);   // :562 | :377, :771
+			if (!go || home) break;
+			if (j == 0 && state != ST_LOW) break;         // only reachable with corrupt pointers: never index s2[-1]
+			const uint32_t nb = pv.nib(i, j);
+			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; em.col(CIG_I, q[i], '-'); }
+			else if (state == ST_MID) {
+				const uint32_t pm = nb & 3u;
+				--i; --j; em.col(CIG_M, q[i], tg[j]);
+				if (pm == 3 && a.mode == MODE_LOCAL) home = true;              // HOME: column emitted, then stop (:788-791)
+				else state = pm;
+			}
+			else if (state == ST_UPP) { state = (nb & 8u) ? ST_UPP : ST_MID; --j; em.col(CIG_D, '-', tg[j]); }
+			else                      { state = pv.jbit(i, j) ? ST_JUMP : ST_MID; --j; em.col(CIG_N, '-', tg[j]); }
+		}
+	}
+	const uint32_t bi = i, bjj = j;
+	if (a.mode == MODE_GLOBAL) {                          // flush (:398-407)
+		while (j > 0) { --j; em.col(CIG_D, '-', tg[j]); }
+		while (i > 0) { --i; em.col(CIG_I, q[i], '-'); }
+	}
+	em.flush_run();
+	if (!em.emit) { a.n_ops[p] = em.n_ops; a.n_cols[p] = em.n_cols; a.beg_i[p] = bi; a.beg_j[p] = bjj; }
+}
+
+// fit+jump: expand the per-pair blacklists into a byte mask aligned with the target bytes.
+__global__ void at_build_jmask(const int32_t *sites, const uint64_t *site_off, const uint64_t *t_off,
+                               const uint32_t *t_len, uint32_t n_pairs, uint8_t *jmask)
+{
+	const uint32_t p = blockIdx.x;
+	if (p >= n_pairs) return;
+	const uint64_t lo = site_off[p], hi = site_off[p + 1];
+	for (uint64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+		const int32_t s = sites[k];
+		if (s >= 0 && (uint32_t)s < t_len[p]) jmask[t_off[p] + s] = 1;
+	}
+}
+
+}  // namespace at

@@ -1,0 +1,713 @@
+// at_runtime.cu -- host runtime behind include/aligntools_b200.h (sections A and C).
+//
+// A batch is sharded over the handle's devices as contiguous slices of pairs (no
+// inter-GPU traffic).  Each shard keeps its sequences resident in HBM,
+// cuts its pairs into CHUNKS whose traceback-pointer blocks fit the pointer arena, and
+// per chunk runs  fill (one launch per rows-per-lane class R)  ->  traceback count walk
+// ->  exclusive scans  ->  traceback emit walk, all on one stream, timed with CUDA events.
+// There is no CPU fallback anywhere in this file: without a usable sm_100 device every
+// entry returns AT_E_CUDA.
+#include "../../../include/aligntools_b200.h"
+#include "at_kernels.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace at;
+
+// ------------------------------------------------------------------ handle ----
+struct at_device {
+	int id = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+};
+
+struct at_handle {
+	std::vector<at_device> devs;
+	std::string err;
+	std::mutex mu;
+	std::atomic<uint64_t> launches{0};
+};
+
+static void set_err(at_handle *h, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+	if (h) { std::lock_guard<std::mutex> g(h->mu); h->err = buf; }
+}
+
+#define CU(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	set_err(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return AT_E_CUDA; } } while (0)
+
+extern "C" void at_default_params(at_params *p)
+{
+	if (!p) return;
+	p->m = 1; p->u = -2; p->o = -5; p->e = -1; p->j = -10; p->jump = 0;   // init_opt, src/alignment.h:105-110
+}
+
+extern "C" const char *at_strerror(int rc)
+{
+	switch (rc) {
+	case AT_OK: return "ok";
+	case AT_E_ARG: return "parameter error";
+	case AT_E_CUDA: return "CUDA error / no usable sm_100 device (there is no CPU fallback)";
+	case AT_E_NOMEM: return "allocation failure";
+	case AT_E_FITLEN: return "first sequence must be shorter than the second to do fitting alignment";
+	case AT_E_NOSPACE: return "output buffer too small";
+	case AT_E_RANGE: return "score range exceeds the int32 lanes";
+	case AT_E_UNDEF: return "input undefined in the reference (empty record, or fit with l2 < 2)";
+	default: return "unknown error";
+	}
+}
+
+extern "C" const char *at_version(void) { return "aligntools-b200 0.1 (sm_100a)"; }
+
+extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
+{
+	if (!out) return AT_E_ARG;
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return AT_E_CUDA;
+	at_handle *h = new at_handle();
+	std::vector<int> ids;
+	if (!devices || n_devices <= 0) ids.push_back(0);
+	else ids.assign(devices, devices + n_devices);
+	for (int id : ids) {
+		if (id < 0 || id >= count) { delete h; return AT_E_ARG; }
+		cudaDeviceProp prop;
+		if (cudaGetDeviceProperties(&prop, id) != cudaSuccess || prop.major < 10) { delete h; return AT_E_CUDA; }
+		at_device d; d.id = id; d.sm_count = prop.multiProcessorCount;
+		if (cudaSetDevice(id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return AT_E_CUDA; }
+		h->devs.push_back(d);
+	}
+	*out = h;
+	return AT_OK;
+}
+
+extern "C" void at_destroy(at_handle *h)
+{
+	if (!h) return;
+	for (auto &d : h->devs) { cudaSetDevice(d.id); if (d.stream) cudaStreamDestroy(d.stream); }
+	delete h;
+}
+
+extern "C" const char *at_last_error(const at_handle *h) { return h ? h->err.c_str() : ""; }
+extern "C" int at_device_count(const at_handle *h) { return h ? (int)h->devs.size() : 0; }
+extern "C" uint64_t at_launch_count(const at_handle *h) { return h ? h->launches.load() : 0; }
+
+// ------------------------------------------------------------------- batch ----
+template <class T> struct DevBuf {
+	T *p = nullptr; size_t n = 0;
+	cudaError_t alloc(size_t count) {
+		if (count <= n && p) return cudaSuccess;
+		release();
+		cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+		if (e == cudaSuccess) n = count; else p = nullptr;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+static const int MAXR = 8;
+
+struct Chunk {
+	uint32_t k0 = 0, k1 = 0;            // shard-local pair range
+	uint64_t ptr_words = 0;
+	std::vector<uint64_t> h_ptr_off;    // chunk-local
+	DevBuf<uint64_t> d_ptr_off;
+	std::vector<uint32_t> h_jobs[MAXR + 1];
+	DevBuf<uint32_t> d_jobs[MAXR + 1];
+	uint64_t cells_r[MAXR + 1] = {0};
+	DevBuf<uint64_t> d_ops_off, d_cols_off;
+	DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_aln1, d_aln2;
+	uint64_t tot_ops = 0, tot_cols = 0;
+};
+
+struct Shard {
+	at_device *dev = nullptr;
+	uint64_t p0 = 0, p1 = 0;            // global pair range
+	uint32_t n = 0;
+	DevBuf<uint8_t> d_q, d_t, d_jmask, d_rclass, d_end_state, d_q2, d_t2;
+	DevBuf<uint64_t> d_q_off, d_t_off, d_site_off;
+	DevBuf<uint32_t> d_q_len, d_t_len, d_end_i, d_end_j, d_beg_i, d_beg_j, d_n_ops, d_n_cols, d_counter;
+	DevBuf<int32_t> d_score, d_sites;
+	DevBuf<uint32_t> d_ptr; DevBuf<int4> d_bnd; DevBuf<uint8_t> d_scan_tmp;
+	std::vector<uint8_t> h_rclass;
+	std::vector<Chunk> chunks;
+	uint32_t max_l2 = 0; bool multi_stripe = false;
+	uint64_t cells = 0, ptr_bytes = 0;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t evk[2] = {nullptr, nullptr};
+	// last-run timing
+	double fill_ms = 0, tb_ms = 0, dev_ms = 0, domk_ms = 0; uint64_t domk_cells = 0, launches = 0;
+	int rc = AT_OK;
+};
+
+struct at_batch {
+	at_handle *h = nullptr;
+	int mode = 0; at_params prm; uint32_t out_flags = 0;
+	uint64_t n = 0;
+	bool traceback = false;
+	std::vector<Shard> shards;
+	bool ran = false;
+};
+
+static inline uint32_t rclass_of(uint32_t l1) { uint32_t r = (l1 + 31) / 32; return r < 1 ? 1 : (r > (uint32_t)MAXR ? MAXR : r); }
+
+static uint64_t ptr_words_of(int mode, bool jump, uint32_t l1, uint32_t l2)
+{
+	const uint32_t R = rclass_of(l1), RPP = 32 * R;
+	const uint64_t stripes = (l1 + RPP - 1) / RPP;
+	if (mode == AT_EDIT) return 0;
+	if (mode == AT_OVERLAP) { const uint32_t tl = (l2 + 31u) | 15u; return stripes * ((tl >> 4) + 1) * RPP; }
+	const uint32_t tl = (l2 + 31u) | (jump ? 31u : 7u);
+	uint64_t w = stripes * ((tl >> 3) + 1) * RPP;
+	if (jump) w += stripes * ((tl >> 5) + 1) * RPP;
+	return w;
+}
+
+__global__ void at_unpack_2bit(const uint8_t *src, const uint64_t *src_off, const uint64_t *dst_off,
+                               const uint32_t *len, uint32_t n_pairs, uint8_t *dst)
+{
+	const uint32_t p = blockIdx.x;
+	if (p >= n_pairs) return;
+	const uint8_t *s = src + src_off[p];
+	uint8_t *d = dst + dst_off[p];
+	for (uint32_t k = threadIdx.x; k < len[p]; k += blockDim.x) {
+		const uint32_t c = (s[k >> 2] >> (2 * (k & 3))) & 3u;
+		d[k] = (uint8_t)("ACGT"[c]);
+	}
+}
+
+// upload one side (reads or targets) of a shard; rewrites offsets relative to the device buffer
+static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t *src, const uint64_t *off,
+                       const uint32_t *len, DevBuf<uint8_t> &d_bytes, DevBuf<uint8_t> &d_packed, DevBuf<uint64_t> &d_off,
+                       DevBuf<uint32_t> &d_len)
+{
+	const uint32_t n = s.n;
+	cudaStream_t st = s.dev->stream;
+	std::vector<uint64_t> rel(n), unp(n);
+	uint64_t lo = UINT64_MAX, hi = 0, tot = 0;
+	bool monotonic = true;
+	for (uint32_t k = 0; k < n; ++k) {
+		const uint64_t o = off[s.p0 + k];
+		const uint64_t nbytes = encoding == AT_SEQ_2BIT ? ((uint64_t)len[s.p0 + k] + 3) / 4 : len[s.p0 + k];
+		if (k && o < hi) monotonic = false;
+		lo = std::min(lo, o); hi = std::max(hi, o + nbytes);
+		unp[k] = tot; tot += len[s.p0 + k];
+	}
+	DevBuf<uint8_t> &raw = encoding == AT_SEQ_2BIT ? d_packed : d_bytes;
+	if (monotonic && hi - lo <= 2 * tot + 64) {          // one bulk copy of the caller's span
+		CU(h, raw.alloc(hi - lo + 16));
+		CU(h, cudaMemcpyAsync(raw.p, src + lo, hi - lo, cudaMemcpyHostToDevice, st));
+		for (uint32_t k = 0; k < n; ++k) rel[k] = off[s.p0 + k] - lo;
+	} else {                                             // scattered records: repack on the host first
+		std::vector<uint8_t> stage;
+		uint64_t pos = 0;
+		for (uint32_t k = 0; k < n; ++k) {
+			const uint64_t nbytes = encoding == AT_SEQ_2BIT ? ((uint64_t)len[s.p0 + k] + 3) / 4 : len[s.p0 + k];
+			rel[k] = pos; stage.resize(pos + nbytes);
+			memcpy(stage.data() + pos, src + off[s.p0 + k], nbytes); pos += nbytes;
+		}
+		CU(h, raw.alloc(pos + 16));
+		CU(h, cudaMemcpyAsync(raw.p, stage.data(), pos, cudaMemcpyHostToDevice, st));
+		CU(h, cudaStreamSynchronize(st));
+	}
+	CU(h, d_off.alloc(n)); CU(h, d_len.alloc(n));
+	CU(h, cudaMemcpyAsync(d_len.p, len + s.p0, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	if (encoding == AT_SEQ_2BIT) {
+		DevBuf<uint64_t> d_src_off;
+		CU(h, d_src_off.alloc(n));
+		CU(h, cudaMemcpyAsync(d_src_off.p, rel.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		CU(h, cudaMemcpyAsync(d_off.p, unp.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		CU(h, d_bytes.alloc(tot + 16));
+		at_unpack_2bit<<<n, 128, 0, st>>>(d_packed.p, d_src_off.p, d_off.p, d_len.p, n, d_bytes.p);
+		CU(h, cudaGetLastError());
+		h->launches++;
+		CU(h, cudaStreamSynchronize(st));
+		d_src_off.release();
+	} else {
+		CU(h, cudaMemcpyAsync(d_off.p, rel.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		CU(h, cudaStreamSynchronize(st));
+	}
+	return AT_OK;
+}
+
+static void free_shard(Shard &s)
+{
+	if (s.dev) cudaSetDevice(s.dev->id);
+	s.d_q.release(); s.d_t.release(); s.d_jmask.release(); s.d_rclass.release(); s.d_end_state.release();
+	s.d_q2.release(); s.d_t2.release();
+	s.d_q_off.release(); s.d_t_off.release(); s.d_site_off.release();
+	s.d_q_len.release(); s.d_t_len.release(); s.d_end_i.release(); s.d_end_j.release(); s.d_beg_i.release();
+	s.d_beg_j.release(); s.d_n_ops.release(); s.d_n_cols.release(); s.d_counter.release();
+	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_bnd.release(); s.d_scan_tmp.release();
+	for (auto &c : s.chunks) {
+		c.d_ptr_off.release(); for (auto &j : c.d_jobs) j.release();
+		c.d_ops_off.release(); c.d_cols_off.release(); c.d_cigar.release(); c.d_aln1.release(); c.d_aln2.release();
+	}
+	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
+}
+
+extern "C" void at_batch_free(at_batch *b)
+{
+	if (!b) return;
+	for (auto &s : b->shards) free_shard(s);
+	delete b;
+}
+
+static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
+{
+	at_handle *h = b->h;
+	CU(h, cudaSetDevice(s.dev->id));
+	cudaStream_t st = s.dev->stream;
+	const uint32_t n = s.n;
+	int rc;
+	if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len))) return rc;
+	if ((rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len))) return rc;
+	s.d_q2.release(); s.d_t2.release();
+	const bool jump = b->mode == AT_FIT && b->prm.jump;
+	if (jump) {
+		uint64_t tot_t = 0;
+		for (uint32_t k = 0; k < n; ++k) tot_t += in->t_len[s.p0 + k];
+		CU(h, s.d_jmask.alloc(s.d_t.n));
+		CU(h, cudaMemsetAsync(s.d_jmask.p, 0, s.d_t.n, st));
+		if (in->sites && in->site_off) {
+			const uint64_t lo = in->site_off[s.p0], hi = in->site_off[s.p1];
+			std::vector<uint64_t> so(n + 1);
+			for (uint32_t k = 0; k <= n; ++k) so[k] = in->site_off[s.p0 + k] - lo;
+			CU(h, s.d_sites.alloc(hi - lo + 1)); CU(h, s.d_site_off.alloc(n + 1));
+			if (hi > lo) CU(h, cudaMemcpyAsync(s.d_sites.p, in->sites + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+			CU(h, cudaMemcpyAsync(s.d_site_off.p, so.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+			at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, s.d_t_off.p, s.d_t_len.p, n, s.d_jmask.p);
+			CU(h, cudaGetLastError());
+			h->launches++;
+			CU(h, cudaStreamSynchronize(st));
+		}
+		(void)tot_t;
+	}
+	// per-pair class, result arrays
+	s.h_rclass.resize(n);
+	s.max_l2 = 0; s.multi_stripe = false; s.cells = 0;
+	for (uint32_t k = 0; k < n; ++k) {
+		const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
+		s.h_rclass[k] = (uint8_t)rclass_of(l1);
+		s.max_l2 = std::max(s.max_l2, l2);
+		if (l1 > 32u * MAXR) s.multi_stripe = true;
+		s.cells += (uint64_t)l1 * l2;
+	}
+	CU(h, s.d_rclass.alloc(n));
+	CU(h, cudaMemcpyAsync(s.d_rclass.p, s.h_rclass.data(), n, cudaMemcpyHostToDevice, st));
+	CU(h, s.d_score.alloc(n)); CU(h, s.d_end_i.alloc(n)); CU(h, s.d_end_j.alloc(n)); CU(h, s.d_end_state.alloc(n));
+	CU(h, s.d_beg_i.alloc(n)); CU(h, s.d_beg_j.alloc(n)); CU(h, s.d_n_ops.alloc(n + 1)); CU(h, s.d_n_cols.alloc(n + 1));
+	CU(h, cudaMemsetAsync(s.d_n_ops.p, 0, (n + 1) * sizeof(uint32_t), st));
+	CU(h, cudaMemsetAsync(s.d_n_cols.p, 0, (n + 1) * sizeof(uint32_t), st));
+	CU(h, cudaMemsetAsync(s.d_beg_i.p, 0, n * sizeof(uint32_t), st));
+	CU(h, cudaMemsetAsync(s.d_beg_j.p, 0, n * sizeof(uint32_t), st));
+	CU(h, s.d_counter.alloc(64));
+
+	// ---- chunking by pointer-arena budget ----
+	size_t free_b = 0, total_b = 0;
+	CU(h, cudaMemGetInfo(&free_b, &total_b));
+	uint64_t budget_words = (uint64_t)(free_b * 0.45) / 4;
+	if (const char *env = getenv("AT_PTR_BUDGET_MB")) budget_words = (uint64_t)atoll(env) * (1ull << 20) / 4;
+	s.chunks.clear();
+	uint64_t max_chunk_words = 0;
+	{
+		Chunk cur; cur.k0 = 0;
+		uint64_t words = 0;
+		for (uint32_t k = 0; k < n; ++k) {
+			const uint64_t w = b->traceback ? ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]) : 0;
+			if (w > budget_words) { set_err(h, "pair %llu needs %llu MB of traceback pointers; arena budget is %llu MB",
+			                                (unsigned long long)(s.p0 + k), (unsigned long long)(w >> 18), (unsigned long long)(budget_words >> 18)); return AT_E_NOMEM; }
+			if (words + w > budget_words && k > cur.k0) {
+				cur.k1 = k; cur.ptr_words = words; s.chunks.push_back(std::move(cur));
+				cur = Chunk(); cur.k0 = k; words = 0;
+			}
+			cur.h_ptr_off.push_back(words);
+			words += w;
+		}
+		cur.k1 = n; cur.ptr_words = words; s.chunks.push_back(std::move(cur));
+	}
+	s.ptr_bytes = 0;
+	for (auto &c : s.chunks) {
+		max_chunk_words = std::max(max_chunk_words, c.ptr_words);
+		s.ptr_bytes += c.ptr_words * 4;
+		const uint32_t nc = c.k1 - c.k0;
+		// job lists per R class, largest pairs first (dynamic queue => good tail balance)
+		std::vector<uint32_t> order(nc);
+		for (uint32_t k = 0; k < nc; ++k) order[k] = c.k0 + k;
+		bool ragged = false;
+		const uint64_t c0 = (uint64_t)in->q_len[s.p0 + c.k0] * in->t_len[s.p0 + c.k0];
+		for (uint32_t k = 1; k < nc && !ragged; ++k)
+			ragged = (uint64_t)in->q_len[s.p0 + c.k0 + k] * in->t_len[s.p0 + c.k0 + k] != c0;
+		if (ragged)
+			std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+				return (uint64_t)in->q_len[s.p0 + x] * in->t_len[s.p0 + x] > (uint64_t)in->q_len[s.p0 + y] * in->t_len[s.p0 + y]; });
+		for (uint32_t k : order) { c.h_jobs[s.h_rclass[k]].push_back(k); c.cells_r[s.h_rclass[k]] += (uint64_t)in->q_len[s.p0 + k] * in->t_len[s.p0 + k]; }
+		for (int r = 1; r <= MAXR; ++r) if (!c.h_jobs[r].empty()) {
+			CU(h, c.d_jobs[r].alloc(c.h_jobs[r].size()));
+			CU(h, cudaMemcpyAsync(c.d_jobs[r].p, c.h_jobs[r].data(), c.h_jobs[r].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+		}
+		CU(h, c.d_ptr_off.alloc(nc));
+		CU(h, cudaMemcpyAsync(c.d_ptr_off.p, c.h_ptr_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		if (b->traceback) { CU(h, c.d_ops_off.alloc(nc + 1)); CU(h, c.d_cols_off.alloc(nc + 1)); }
+		CU(h, cudaStreamSynchronize(st));
+	}
+	if (max_chunk_words) {
+		cudaError_t e = s.d_ptr.alloc(max_chunk_words);
+		if (e != cudaSuccess) { set_err(h, "pointer arena of %llu MB: %s", (unsigned long long)(max_chunk_words >> 18), cudaGetErrorString(e)); return AT_E_NOMEM; }
+	}
+	for (auto &e : s.ev) CU(h, cudaEventCreate(&e));
+	for (auto &e : s.evk) CU(h, cudaEventCreate(&e));
+	return AT_OK;
+}
+
+extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
+                               uint32_t out_flags, at_batch **out)
+{
+	if (!h || !p || !in || !out) return AT_E_ARG;
+	*out = nullptr;
+	if (mode < AT_GLOBAL || mode > AT_EDIT) { set_err(h, "bad mode %d", mode); return AT_E_ARG; }
+	if (!in->n_pairs || !in->q || !in->q_off || !in->q_len || !in->t || !in->t_off || !in->t_len) { set_err(h, "align: parameter error"); return AT_E_ARG; }
+	if (in->encoding != AT_SEQ_BYTES && in->encoding != AT_SEQ_2BIT) return AT_E_ARG;
+	if ((in->sites == nullptr) != (in->site_off == nullptr)) return AT_E_ARG;
+	if (in->n_pairs >= (1ull << 31)) return AT_E_ARG;
+	// validation mirrors the reference's own failure modes
+	int64_t maxabs = std::max<int64_t>({llabs((long long)p->m), llabs((long long)p->u), llabs((long long)p->o), llabs((long long)p->e), llabs((long long)p->j), 1});
+	for (uint64_t k = 0; k < in->n_pairs; ++k) {
+		const uint64_t l1 = in->q_len[k], l2 = in->t_len[k];
+		if (l1 == 0 || l2 == 0) { set_err(h, "pair %llu: empty record", (unsigned long long)k); return AT_E_UNDEF; }
+		if (mode == AT_FIT && l1 > l2) { set_err(h, "pair %llu: first sequence must be shorter than the second to do fitting alignment", (unsigned long long)k); return AT_E_FITLEN; }
+		if (mode == AT_FIT && l2 < 2) { set_err(h, "pair %llu: fit with l2 < 2 is undefined in the reference", (unsigned long long)k); return AT_E_UNDEF; }
+		if ((int64_t)(l1 + l2 + 2) * maxabs >= (1ll << 27)) { set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
+	}
+	at_batch *b = new at_batch();
+	b->h = h; b->mode = mode; b->prm = *p; b->out_flags = out_flags; b->n = in->n_pairs;
+	b->traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
+	// contiguous slices balanced by cells
+	const size_t nd = h->devs.size();
+	std::vector<uint64_t> cut(nd + 1, 0);
+	{
+		long double total = 0;
+		for (uint64_t k = 0; k < b->n; ++k) total += (long double)in->q_len[k] * in->t_len[k];
+		long double acc = 0; size_t d = 1;
+		for (uint64_t k = 0; k < b->n && d < nd; ++k) {
+			acc += (long double)in->q_len[k] * in->t_len[k];
+			while (d < nd && acc >= total * d / nd) { cut[d++] = k + 1; }
+		}
+		for (; d < nd; ++d) cut[d] = b->n;
+		cut[nd] = b->n;
+	}
+	b->shards.resize(nd);
+	std::vector<std::thread> th;
+	for (size_t d = 0; d < nd; ++d) {
+		Shard &s = b->shards[d];
+		s.dev = &h->devs[d]; s.p0 = cut[d]; s.p1 = cut[d + 1]; s.n = (uint32_t)(s.p1 - s.p0);
+	}
+	auto work = [&](size_t d) { Shard &s = b->shards[d]; s.rc = s.n ? setup_shard(b, s, in) : AT_OK; };
+	if (nd == 1) work(0);
+	else { for (size_t d = 0; d < nd; ++d) th.emplace_back(work, d); for (auto &t : th) t.join(); }
+	for (auto &s : b->shards) if (s.rc) { int rc = s.rc; at_batch_free(b); return rc; }
+	*out = b;
+	return AT_OK;
+}
+
+// ------------------------------------------------------------------ launch ----
+template <int MODE, bool JUMP> struct AffineLauncher {
+	template <int R> static cudaError_t go(const FillArgs &fa, int blocks, cudaStream_t st) {
+		at_fill_affine<MODE, R, JUMP><<<blocks, 128, 0, st>>>(fa);
+		return cudaGetLastError();
+	}
+	template <int R> static int occ() {
+		int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_affine<MODE, R, JUMP>, 128, 0); return nb;
+	}
+};
+template <int MODE> struct LinearLauncher {
+	template <int R> static cudaError_t go(const FillArgs &fa, int blocks, cudaStream_t st) {
+		at_fill_linear<MODE, R><<<blocks, 128, 0, st>>>(fa);
+		return cudaGetLastError();
+	}
+	template <int R> static int occ() {
+		int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_linear<MODE, R>, 128, 0); return nb;
+	}
+};
+
+template <class L> static int occ_r(int R)
+{
+	switch (R) {
+	case 1: return L::template occ<1>(); case 2: return L::template occ<2>(); case 3: return L::template occ<3>();
+	case 4: return L::template occ<4>(); case 5: return L::template occ<5>(); case 6: return L::template occ<6>();
+	case 7: return L::template occ<7>(); default: return L::template occ<8>();
+	}
+}
+template <class L> static cudaError_t go_r(int R, const FillArgs &fa, int blocks, cudaStream_t st)
+{
+	switch (R) {
+	case 1: return L::template go<1>(fa, blocks, st); case 2: return L::template go<2>(fa, blocks, st);
+	case 3: return L::template go<3>(fa, blocks, st); case 4: return L::template go<4>(fa, blocks, st);
+	case 5: return L::template go<5>(fa, blocks, st); case 6: return L::template go<6>(fa, blocks, st);
+	case 7: return L::template go<7>(fa, blocks, st); default: return L::template go<8>(fa, blocks, st);
+	}
+}
+
+static int fill_occupancy(int mode, bool jump, int R)
+{
+	switch (mode) {
+	case AT_GLOBAL: return occ_r<AffineLauncher<MODE_GLOBAL, false>>(R);
+	case AT_LOCAL:  return occ_r<AffineLauncher<MODE_LOCAL, false>>(R);
+	case AT_FIT:    return jump ? occ_r<AffineLauncher<MODE_FIT, true>>(R) : occ_r<AffineLauncher<MODE_FIT, false>>(R);
+	case AT_OVERLAP: return occ_r<LinearLauncher<MODE_OVERLAP>>(R);
+	default:        return occ_r<LinearLauncher<MODE_EDIT>>(R);
+	}
+}
+static cudaError_t fill_launch(int mode, bool jump, int R, const FillArgs &fa, int blocks, cudaStream_t st)
+{
+	switch (mode) {
+	case AT_GLOBAL: return go_r<AffineLauncher<MODE_GLOBAL, false>>(R, fa, blocks, st);
+	case AT_LOCAL:  return go_r<AffineLauncher<MODE_LOCAL, false>>(R, fa, blocks, st);
+	case AT_FIT:    return jump ? go_r<AffineLauncher<MODE_FIT, true>>(R, fa, blocks, st) : go_r<AffineLauncher<MODE_FIT, false>>(R, fa, blocks, st);
+	case AT_OVERLAP: return go_r<LinearLauncher<MODE_OVERLAP>>(R, fa, blocks, st);
+	default:        return go_r<LinearLauncher<MODE_EDIT>>(R, fa, blocks, st);
+	}
+}
+
+struct CastU64 { __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; } };
+
+static int run_shard(at_batch *b, Shard &s)
+{
+	at_handle *h = b->h;
+	CU(h, cudaSetDevice(s.dev->id));
+	cudaStream_t st = s.dev->stream;
+	const bool jump = b->mode == AT_FIT && b->prm.jump;
+	s.fill_ms = s.tb_ms = s.dev_ms = s.domk_ms = 0; s.domk_cells = 0; s.launches = 0;
+	// dominant (most cells) fill launch of the whole shard -> per-launch timing for the roofline
+	int dom_chunk = -1, dom_r = -1; uint64_t dom_cells = 0;
+	for (size_t ci = 0; ci < s.chunks.size(); ++ci)
+		for (int r = 1; r <= MAXR; ++r) if (s.chunks[ci].cells_r[r] > dom_cells) { dom_cells = s.chunks[ci].cells_r[r]; dom_chunk = (int)ci; dom_r = r; }
+
+	cudaEvent_t e_begin = s.ev[0], e_fill = s.ev[1], e_tb = s.ev[2];
+	float ms = 0;
+	bool first = true;
+	cudaEvent_t e_first = s.ev[3];
+	for (size_t ci = 0; ci < s.chunks.size(); ++ci) {
+		Chunk &c = s.chunks[ci];
+		const uint32_t nc = c.k1 - c.k0;
+		CU(h, cudaMemsetAsync(s.d_counter.p, 0, 64 * sizeof(uint32_t), st));
+		CU(h, cudaEventRecord(e_begin, st));
+		if (first) { CU(h, cudaEventRecord(e_first, st)); first = false; }
+		for (int r = 1; r <= MAXR; ++r) {
+			if (c.h_jobs[r].empty()) continue;
+			int occ = fill_occupancy(b->mode, jump, r);
+			if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, r); return AT_E_CUDA; }
+			const uint64_t warps_needed = c.h_jobs[r].size();
+			int blocks = s.dev->sm_count * occ;
+			blocks = (int)std::min<uint64_t>((uint64_t)blocks, (warps_needed + 3) / 4);
+			if (blocks < 1) blocks = 1;
+			if (s.multi_stripe) {
+				const uint64_t stride = (uint64_t)s.max_l2 + 2;
+				CU(h, s.d_bnd.alloc((size_t)s.dev->sm_count * 16 * 4 * stride > 0 ? (size_t)s.dev->sm_count * 16 * 4 * stride : 1));
+			} else CU(h, s.d_bnd.alloc(1));
+			FillArgs fa;
+			fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
+			fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
+			fa.jmask = s.d_jmask.p; fa.jobs = c.d_jobs[r].p; fa.n_jobs = (uint32_t)c.h_jobs[r].size();
+			fa.counter = s.d_counter.p + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
+			fa.bnd = s.d_bnd.p; fa.bnd_stride = s.max_l2 + 2;
+			fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
+			fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
+			fa.want_ptr = b->traceback ? 1 : 0;
+			if (blocks > s.dev->sm_count * 16) blocks = s.dev->sm_count * 16;   // bnd slabs are sized for 16 blocks/SM
+			const bool dom = (int)ci == dom_chunk && r == dom_r;
+			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
+			CU(h, fill_launch(b->mode, jump, r, fa, blocks, st));
+			if (dom) CU(h, cudaEventRecord(s.evk[1], st));
+			s.launches++;
+		}
+		CU(h, cudaEventRecord(e_fill, st));
+		if (b->traceback) {
+			TraceArgs ta;
+			ta.q = s.d_q.p; ta.q_off = s.d_q_off.p; ta.q_len = s.d_q_len.p;
+			ta.t = s.d_t.p; ta.t_off = s.d_t_off.p; ta.t_len = s.d_t_len.p;
+			ta.ptr = s.d_ptr.p; ta.ptr_off = c.d_ptr_off.p; ta.rclass = s.d_rclass.p;
+			ta.pair_base = c.k0; ta.n_pairs = nc;
+			ta.end_i = s.d_end_i.p; ta.end_j = s.d_end_j.p; ta.end_state = s.d_end_state.p;
+			ta.beg_i = s.d_beg_i.p; ta.beg_j = s.d_beg_j.p; ta.n_ops = s.d_n_ops.p; ta.n_cols = s.d_n_cols.p;
+			ta.ops_off = c.d_ops_off.p; ta.cols_off = c.d_cols_off.p;
+			ta.cigar = nullptr; ta.aln1 = nullptr; ta.aln2 = nullptr;
+			ta.mode = b->mode; ta.jump = jump ? 1 : 0; ta.emit = 0;
+			const int tb_blocks = (int)((nc + 127) / 128);
+			at_traceback<<<tb_blocks, 128, 0, st>>>(ta);
+			CU(h, cudaGetLastError());
+			s.launches++;
+			// exclusive scans (CUB): n_ops[k0..k1) + trailing slot -> offsets[nc+1]
+			size_t tmp_bytes = 0;
+			cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_ops(s.d_n_ops.p + c.k0, CastU64());
+			cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_cols(s.d_n_cols.p + c.k0, CastU64());
+			// the slot after the chunk must read as zero for the total: scan nc items and add the tail on the host
+			CU(h, cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
+			CU(h, s.d_scan_tmp.alloc(tmp_bytes + 16));
+			CU(h, cudaMemsetAsync(c.d_ops_off.p, 0, sizeof(uint64_t), st));
+			CU(h, cudaMemsetAsync(c.d_cols_off.p, 0, sizeof(uint64_t), st));
+			CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
+			CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_cols, c.d_cols_off.p + 1, (int)nc, st));
+			uint64_t tot[2] = {0, 0};
+			CU(h, cudaMemcpyAsync(&tot[0], c.d_ops_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			CU(h, cudaMemcpyAsync(&tot[1], c.d_cols_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			CU(h, cudaStreamSynchronize(st));
+			c.tot_ops = tot[0]; c.tot_cols = tot[1];
+			const bool want_cig = b->out_flags & AT_OUT_CIGAR, want_aln = b->out_flags & AT_OUT_ALN;
+			if (want_cig) { if (c.d_cigar.alloc(c.tot_ops + 1) != cudaSuccess) { set_err(h, "cigar buffer"); return AT_E_NOMEM; } }
+			if (want_aln) { if (c.d_aln1.alloc(c.tot_cols + 1) != cudaSuccess || c.d_aln2.alloc(c.tot_cols + 1) != cudaSuccess) { set_err(h, "alignment buffer"); return AT_E_NOMEM; } }
+			ta.cigar = want_cig ? c.d_cigar.p : nullptr;
+			ta.aln1 = want_aln ? c.d_aln1.p : nullptr; ta.aln2 = want_aln ? c.d_aln2.p : nullptr;
+			ta.emit = 1;
+			at_traceback<<<tb_blocks, 128, 0, st>>>(ta);
+			CU(h, cudaGetLastError());
+			s.launches++;
+		}
+		CU(h, cudaEventRecord(e_tb, st));
+		CU(h, cudaStreamSynchronize(st));
+		CU(h, cudaEventElapsedTime(&ms, e_begin, e_fill)); s.fill_ms += ms;
+		CU(h, cudaEventElapsedTime(&ms, e_fill, e_tb)); s.tb_ms += ms;
+		if ((int)ci == dom_chunk) { CU(h, cudaEventElapsedTime(&ms, s.evk[0], s.evk[1])); s.domk_ms = ms; s.domk_cells = dom_cells; }
+		if (ci + 1 == s.chunks.size()) { CU(h, cudaEventElapsedTime(&ms, e_first, e_tb)); s.dev_ms = ms; }
+	}
+	h->launches += s.launches;
+	return AT_OK;
+}
+
+extern "C" int at_batch_run(at_batch *b, at_timing *timing)
+{
+	if (!b) return AT_E_ARG;
+	const size_t nd = b->shards.size();
+	auto work = [&](size_t d) { Shard &s = b->shards[d]; s.rc = s.n ? run_shard(b, s) : AT_OK; };
+	if (nd == 1) work(0);
+	else { std::vector<std::thread> th; for (size_t d = 0; d < nd; ++d) th.emplace_back(work, d); for (auto &t : th) t.join(); }
+	for (auto &s : b->shards) if (s.rc) return s.rc;
+	b->ran = true;
+	if (timing) {
+		memset(timing, 0, sizeof *timing);
+		for (auto &s : b->shards) {
+			timing->fill_ms = std::max(timing->fill_ms, s.fill_ms);
+			timing->traceback_ms = std::max(timing->traceback_ms, s.tb_ms);
+			timing->device_ms = std::max(timing->device_ms, s.dev_ms);
+			timing->cells += s.cells; timing->launches += s.launches; timing->ptr_bytes += b->traceback ? s.ptr_bytes : 0;
+			if (s.domk_cells > timing->fill_kernel_cells) { timing->fill_kernel_cells = s.domk_cells; timing->fill_kernel_ms = s.domk_ms; }
+		}
+	}
+	return AT_OK;
+}
+
+extern "C" int at_batch_sizes(const at_batch *b, uint64_t *cigar_ops, uint64_t *aln_bytes)
+{
+	if (!b || !b->ran) return AT_E_ARG;
+	uint64_t o = 0, c = 0;
+	for (auto &s : b->shards) for (auto &ch : s.chunks) { o += ch.tot_ops; c += ch.tot_cols; }
+	if (cigar_ops) *cigar_ops = (b->out_flags & AT_OUT_CIGAR) ? o : 0;
+	if (aln_bytes) *aln_bytes = (b->out_flags & AT_OUT_ALN) ? c : 0;
+	return AT_OK;
+}
+
+extern "C" int at_batch_fetch(at_batch *b, at_batch_output *out)
+{
+	if (!b || !out || !b->ran || !out->score) return AT_E_ARG;
+	at_handle *h = b->h;
+	const bool want_cig = b->traceback && (b->out_flags & AT_OUT_CIGAR) && out->cigar;
+	const bool want_aln = b->traceback && (b->out_flags & AT_OUT_ALN) && out->aln1 && out->aln2;
+	if (want_cig && !out->cigar_off) return AT_E_ARG;
+	if (want_aln && !out->aln_off) return AT_E_ARG;
+	uint64_t tot_ops = 0, tot_cols = 0;
+	at_batch_sizes(b, &tot_ops, &tot_cols);
+	if (want_cig && tot_ops > out->cigar_cap) { set_err(h, "cigar buffer too small: need %llu ops", (unsigned long long)tot_ops); return AT_E_NOSPACE; }
+	if (want_aln && tot_cols > out->aln_cap) { set_err(h, "alignment buffer too small: need %llu bytes", (unsigned long long)tot_cols); return AT_E_NOSPACE; }
+	uint64_t base_ops = 0, base_cols = 0;
+	std::vector<uint64_t> tmp;
+	for (auto &s : b->shards) {
+		if (!s.n) continue;
+		CU(h, cudaSetDevice(s.dev->id));
+		cudaStream_t st = s.dev->stream;
+		CU(h, cudaMemcpyAsync(out->score + s.p0, s.d_score.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+		if (out->end_i) CU(h, cudaMemcpyAsync(out->end_i + s.p0, s.d_end_i.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		if (out->end_j) CU(h, cudaMemcpyAsync(out->end_j + s.p0, s.d_end_j.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		if (out->beg_i) CU(h, cudaMemcpyAsync(out->beg_i + s.p0, s.d_beg_i.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		if (out->beg_j) CU(h, cudaMemcpyAsync(out->beg_j + s.p0, s.d_beg_j.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		for (auto &c : s.chunks) {
+			const uint32_t nc = c.k1 - c.k0;
+			if (want_cig) {
+				CU(h, cudaMemcpyAsync(out->cigar_off + s.p0 + c.k0, c.d_ops_off.p, (nc + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+				if (c.tot_ops) CU(h, cudaMemcpyAsync(out->cigar + base_ops, c.d_cigar.p, c.tot_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+			}
+			if (want_aln) {
+				CU(h, cudaMemcpyAsync(out->aln_off + s.p0 + c.k0, c.d_cols_off.p, (nc + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+				if (c.tot_cols) {
+					CU(h, cudaMemcpyAsync(out->aln1 + base_cols, c.d_aln1.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
+					CU(h, cudaMemcpyAsync(out->aln2 + base_cols, c.d_aln2.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
+				}
+			}
+			CU(h, cudaStreamSynchronize(st));
+			// chunk-local offsets -> global
+			if (want_cig && base_ops) for (uint32_t k = 0; k <= nc; ++k) out->cigar_off[s.p0 + c.k0 + k] += base_ops;
+			if (want_aln && base_cols) for (uint32_t k = 0; k <= nc; ++k) out->aln_off[s.p0 + c.k0 + k] += base_cols;
+			base_ops += c.tot_ops; base_cols += c.tot_cols;
+		}
+		CU(h, cudaStreamSynchronize(st));
+	}
+	if (!b->traceback) {
+		if (out->cigar_off) for (uint64_t k = 0; k <= b->n; ++k) out->cigar_off[k] = 0;
+		if (out->aln_off) for (uint64_t k = 0; k <= b->n; ++k) out->aln_off[k] = 0;
+	}
+	return AT_OK;
+}
+
+extern "C" int at_batch_align(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
+                              uint32_t out_flags, at_batch_output *out, at_timing *timing)
+{
+	at_batch *b = nullptr;
+	int rc = at_batch_create(h, mode, p, in, out_flags, &b);
+	if (rc) return rc;
+	rc = at_batch_run(b, timing);
+	if (!rc) rc = at_batch_fetch(b, out);
+	at_batch_free(b);
+	return rc;
+}
+
+extern "C" int64_t at_pack_2bit(const char *seq, uint64_t n, uint8_t *dst)
+{
+	if (!seq || !dst) return -1;
+	const uint64_t nb = (n + 3) / 4;
+	memset(dst, 0, nb);
+	for (uint64_t k = 0; k < n; ++k) {
+		uint8_t c;
+		switch (seq[k]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break; default: return -1; }
+		dst[k >> 2] |= (uint8_t)(c << (2 * (k & 3)));
+	}
+	return (int64_t)nb;
+}
+
+extern "C" int64_t at_cigar_to_string(const uint32_t *ops, uint64_t n_ops, char *dst, uint64_t cap)
+{
+	if (!dst || (!ops && n_ops)) return -1;
+	uint64_t pos = 0;
+	for (uint64_t k = 0; k < n_ops; ++k) {
+		char buf[16];
+		const int len = snprintf(buf, sizeof buf, "%u%c", ops[k] >> 4, "MIDN"[ops[k] & 3]);
+		if (pos + len + 1 > cap) return -1;
+		memcpy(dst + pos, buf, len); pos += len;
+	}
+	if (pos + 1 > cap) return -1;
+	dst[pos] = 0;
+	return (int64_t)pos;
+}

@@ -193,7 +193,7 @@ static int affine_align(int mode, const uint8_t *s1, size_t l1, const uint8_t *s
 				int p = PJ[(size_t)ti * W + tj]; state = p == 1 ? P_MID : p == 2 ? P_JUMP : P_NONE;
 				r1[cur] = '-'; r2[cur] = (char)s2[--tj]; if (ops) ops[cur] = 'N'; cur++;
 			} else if (state == P_HOME && mode == AT_LOCAL) {
-				ti = 0; tj = 0;
+				break;   /* the reference sets i = j = 0 (:788-791); beg_i/beg_j report where the walk stopped */
 			} else { /* unset pointer: the reference would spin forever; cannot happen on a finite path */
 				free(P); free(PJ); free(smask); free(buf); return -4;
 			}

@@ -1,0 +1,220 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C-ABI library
+(aligntools/c_b200/libaligntools_b200.so); the oracle is only the checker."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from helpers import (expected_stdout, load_cli, load_fuzz, pack_batch, parse_cli_argv,
+                     sites_from_comment)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A():
+    import aligntools.c_b200 as A
+    return A
+
+
+@pytest.fixture(scope="module")
+def aligner(A):
+    al = A.Aligner()
+    yield al
+    al.close()
+
+
+def rle(ops: bytes) -> str:
+    out, k = [], 0
+    while k < len(ops):
+        j = k
+        while j < len(ops) and ops[j] == ops[k]:
+            j += 1
+        out.append(f"{j - k}{chr(ops[k])}")
+        k = j
+    return "".join(out)
+
+
+def check_batch_vs_port(A, aligner, oracle_mod, mode, prm, q, qo, ql, t, to, tl, sites=None, site_off=None,
+                        encoding=0, threads=8, q_dev=None, qo_dev=None, t_dev=None, to_dev=None):
+    opt = A.Opt(**prm)
+    p = oracle_mod.Params(prm["m"], prm["u"], prm["o"], prm["e"], prm["j"], prm["jump"])
+    ref = oracle_mod.port_batch(mode, p, q, np.append(qo, 0).astype(np.uint64), ql, t, np.append(to, 0).astype(np.uint64), tl,
+                                sites, site_off, want_aln=(mode != "edit"), want_ops=(mode != "edit"), threads=threads)
+    b = aligner.batch(mode, opt, q if q_dev is None else q_dev, qo if qo_dev is None else qo_dev, ql,
+                      t if t_dev is None else t_dev, to if to_dev is None else to_dev, tl,
+                      sites=sites, site_off=site_off, encoding=encoding)
+    tm = b.run()
+    res = b.fetch()
+    b.free()
+    n = len(ql)
+    assert tm.cells == int((ql.astype(np.uint64) * tl.astype(np.uint64)).sum())
+    bad = np.nonzero(res.score.astype(np.int64) != ref.score)[0]
+    assert bad.size == 0, (mode, "score mismatch at", bad[:5], res.score[bad[:5]], ref.score[bad[:5]])
+    if mode == "edit":
+        return tm
+    assert np.array_equal(res.end_i, ref.coords[:, 0].astype(np.uint32))
+    assert np.array_equal(res.end_j, ref.coords[:, 1].astype(np.uint32))
+    for k in range(n):
+        assert res.aln(k) == ref.aln(k), (mode, k)
+        assert res.cigar_string(k) == rle(ref.op(k)), (mode, k)
+    return tm
+
+
+def test_golden_cli_vectors_through_cabi(A, aligner):
+    """Config 1 (B1) and the other 26 rc==0 golden commands: stdout rebuilt from the GPU result
+    must hash to the reference's md5."""
+    gold = load_cli()
+    n = 0
+    for v in gold["vectors"]:
+        if v["rc"] != 0:
+            continue
+        mode, prm, fname = parse_cli_argv(v["argv"])
+        recs = gold["files"][fname.split("/")[-1]]["records"]
+        s1, s2 = recs[0]["seq"].encode(), recs[1]["seq"].encode()
+        comment = recs[1]["comment"] or ""
+        opt = A.Opt(**prm)
+        sites = [sites_from_comment(comment)] if (mode == "fit" and prm["jump"]) else None
+        res = aligner.align(mode, [s1], [s2], opt, sites=sites, out_flags=0 if mode == "edit" else 3)
+        r1, r2 = (b"", b"") if mode == "edit" else res.aln(0)
+        out = expected_stdout(mode, prm, comment, int(res.score[0]), r1, r2)
+        assert hashlib.md5(out).hexdigest() == v["stdout_md5"], (v["id"], out[:80])
+        n += 1
+    assert n >= 27
+
+
+def test_fuzz_fixtures(A, aligner):
+    """900 reference-answered cases, all six mode variants, random (also sign-flipped) params."""
+    for c in load_fuzz():
+        opt = A.Opt(c["m"], c["u"], c["o"], c["e"], c["j"], bool(c["jump"]))
+        sites = [c["sites"] or []] if c["jump"] else None
+        res = aligner.align(c["mode"], [c["s1"].encode("latin-1")], [c["s2"].encode("latin-1")], opt, sites=sites,
+                            out_flags=0 if c["mode"] == "edit" else 3)
+        assert int(res.score[0]) == c["score"], c
+        if c["mode"] != "edit":
+            assert res.aln(0) == (c["r1"].encode("latin-1"), c["r2"].encode("latin-1")), c
+
+
+def _random_batch(rng, n, l1_rng, extra_rng, alphabet=b"ACGT", fit=False):
+    q, t = [], []
+    for _ in range(n):
+        l1 = rng.randint(*l1_rng)
+        s1 = bytes(rng.choice(alphabet) for _ in range(l1))
+        mut = bytearray()
+        for ch in s1:
+            r = rng.random()
+            if r < 0.06:
+                mut.append(rng.choice(alphabet))
+            elif r < 0.08:
+                continue
+            elif r < 0.10:
+                mut.append(ch); mut.append(rng.choice(alphabet))
+            else:
+                mut.append(ch)
+        s2 = bytes(rng.choice(alphabet) for _ in range(rng.randint(*extra_rng))) + bytes(mut) + \
+            bytes(rng.choice(alphabet) for _ in range(rng.randint(1, extra_rng[1] + 1)))
+        if fit and len(s1) > len(s2):
+            s1, s2 = s2, s1
+        q.append(s1); t.append(s2)
+    return q, t
+
+
+@pytest.mark.parametrize("mode", ["global", "local", "fit", "fitjump", "overlap", "edit"])
+def test_ragged_batches_all_row_classes(A, aligner, oracle_mod, mode):
+    """Ragged batch covering every rows-per-lane class (l1 1..256) and multi-stripe reads
+    (l1 up to 900), each pair checked against the oracle: score, end cell, r1/r2, CIGAR."""
+    rng = random.Random(1234 + len(mode))
+    q, t = _random_batch(rng, 300, (1, 300), (0, 120), fit=mode.startswith("fit"))
+    q2, t2 = _random_batch(rng, 40, (257, 900), (0, 300), fit=mode.startswith("fit"))
+    q += q2; t += t2
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    prm = dict(m=2, u=-3, o=-4, e=-1, j=-7, jump=(mode == "fitjump"))
+    sites = site_off = None
+    if mode == "fitjump":
+        ss, so = [], [0]
+        for s2 in t:
+            k = rng.choice([0, 1, 3, 8])
+            ss += sorted(rng.randrange(len(s2)) for _ in range(k)); so.append(len(ss))
+        sites = np.array(ss + [0], dtype=np.int32); site_off = np.array(so, dtype=np.uint64)
+    md = "fit" if mode == "fitjump" else mode
+    check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites, site_off)
+
+
+def test_config2_shape_20k_pairs(A, aligner, oracle_mod):
+    """BASELINE config 2 shape (local, 150 x 500, README local params) on 20 000 pairs."""
+    from aligntools.c_b200 import synth
+    w = synth.config2_local(n_pairs=20000)
+    tm = check_batch_vs_port(A, aligner, oracle_mod, "local", w["params"], w["q"], w["q_off"], w["q_len"],
+                             w["t"], w["t_off"], w["t_len"])
+    assert tm.launches >= 3 and tm.ptr_bytes > 0
+
+
+def test_config2_2bit_encoding(A, aligner, oracle_mod):
+    """Same workload handed over as 2-bit packed device buffers (AT_SEQ_2BIT)."""
+    from aligntools.c_b200 import synth
+    w = synth.config2_local(n_pairs=3000, stream=1)
+    q2, qo2, _ = A.pack_2bit(w["q"], w["q_off"], w["q_len"])
+    t2, to2, _ = A.pack_2bit(w["t"], w["t_off"], w["t_len"])
+    check_batch_vs_port(A, aligner, oracle_mod, "local", w["params"], w["q"], w["q_off"], w["q_len"],
+                        w["t"], w["t_off"], w["t_len"], encoding=1, q_dev=q2, qo_dev=qo2, t_dev=t2, to_dev=to2)
+
+
+def test_config3_shape_fit_jump(A, aligner, oracle_mod):
+    """BASELINE config 3 shape: fit -s -j -10, 2 kbp transcripts vs 20 kbp two-gene targets."""
+    from aligntools.c_b200 import synth
+    w = synth.config3_fit_jump(n_pairs=6)
+    check_batch_vs_port(A, aligner, oracle_mod, "fit", w["params"], w["q"], w["q_off"], w["q_len"],
+                        w["t"], w["t_off"], w["t_len"], w["sites"], w["site_off"])
+
+
+def test_config4_shape_overlap(A, aligner, oracle_mod):
+    """BASELINE config 4 shape at reduced length (3-6 kbp long-read pairs)."""
+    from aligntools.c_b200 import synth
+    w = synth.config4_overlap(n_pairs=6, lo=3000, hi=6000)
+    check_batch_vs_port(A, aligner, oracle_mod, "overlap", w["params"], w["q"], w["q_off"], w["q_len"],
+                        w["t"], w["t_off"], w["t_len"])
+
+
+def test_config5_shape_edit(A, aligner, oracle_mod):
+    """BASELINE config 5 shape at reduced length (20 kbp pairs)."""
+    from aligntools.c_b200 import synth
+    w = synth.config5_edit(n_pairs=4, length=20000)
+    check_batch_vs_port(A, aligner, oracle_mod, "edit", w["params"], w["q"], w["q_off"], w["q_len"],
+                        w["t"], w["t_off"], w["t_len"])
+
+
+def test_chunked_pointer_arena(A, aligner, oracle_mod, monkeypatch):
+    """Force several chunks (tiny pointer arena) and scattered, non-monotonic input offsets."""
+    from aligntools.c_b200 import synth
+    monkeypatch.setenv("AT_PTR_BUDGET_MB", "8")
+    w = synth.config2_local(n_pairs=1500, stream=2)
+    perm = np.random.default_rng(5).permutation(1500)
+    check_batch_vs_port(A, aligner, oracle_mod, "local", w["params"], w["q"], w["q_off"][perm].copy(), w["q_len"],
+                        w["t"], w["t_off"][perm].copy(), w["t_len"])
+
+
+def test_error_codes(A, aligner):
+    with pytest.raises(A.AtError) as e:
+        aligner.align("fit", [b"ACGTACGT"], [b"ACG"])
+    assert e.value.rc == -4          # AT_E_FITLEN, reference dies at :599
+    with pytest.raises(A.AtError) as e:
+        aligner.align("local", [b""], [b"ACG"])
+    assert e.value.rc == -7
+    with pytest.raises(A.AtError) as e:
+        aligner.align("fit", [b"A"], [b"A"])
+    assert e.value.rc == -7
+
+
+def test_reference_named_operators(A):
+    """Single-pair operators with the reference's names (README examples)."""
+    sc, r1, r2 = A.align_local_affine(b"PLEASANTLY", b"MEANLY", A.Opt(m=2, u=-2, o=-5, e=-2))
+    assert (sc, r1, r2) == (4.0, b"LEA", b"MEA")                      # golden B5
+    sc, r1, r2 = A.align_gla(b"PLEASANTLY", b"MEANLY")
+    assert (sc, r1, r2) == (-12.0, b"PLEASANTLY", b"M-EAN---LY")      # golden B3
+    assert A.edit_dist(b"PLEASANTLY", b"MEANLY", A.Opt(u=1)) == 5      # golden B22
+    sc, r1, r2 = A.align_overlap(b"PLEASANTLY", b"MEANLY")
+    assert (sc, r1, r2) == (0.0, b"", b"")                             # golden B16
+    with pytest.raises(ValueError):
+        A.align_fit_affine_jump(b"PLEASANTLY", b"MEANLY")
