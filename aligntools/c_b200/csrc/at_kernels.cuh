@@ -358,7 +358,8 @@ struct TraceArgs {
 	const uint8_t  *q;  const uint64_t *q_off;  const uint32_t *q_len;
 	const uint8_t  *t;  const uint64_t *t_off;  const uint32_t *t_len;
 	const uint32_t *ptr; const uint64_t *ptr_off;
-	const uint8_t  *rclass;    // [pair] rows-per-lane R the fill used for the pair
+	const uint8_t  *rclass;    // [pair] bits 0-3: rows-per-lane R the fill used; bits 4-5: 0 = int32 layout,
+	                           //        1 / 2 = packed s16x2 layout, pair in the low / high half (at_kernels_p16.cuh)
 	uint32_t        pair_base, n_pairs;   // chunk
 	const uint32_t *end_i, *end_j; const uint8_t *end_state;
 	uint32_t       *beg_i, *beg_j;
@@ -371,9 +372,13 @@ struct TraceArgs {
 
 struct PtrView {
 	const uint32_t *ptr, *ptrJ;
-	uint32_t R, RPP, G, GJ;
+	uint32_t R, RPP, G, GJ, half;
 	__device__ __forceinline__ uint32_t nib(uint32_t i, uint32_t j) const {
 		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
+		if (half) {   // packed s16x2: 4 steps x 2 pairs per word, single stripe
+			const uint32_t w = __ldg(ptr + ((size_t)(t >> 2) * R + r) * 32 + lane);
+			return (w >> (16 * (half - 1) + 4 * (3 - (t & 3)))) & 15u;
+		}
 		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 3)) * R + r) * 32 + lane);
 		return (w >> (4 * (7 - (t & 7)))) & 15u;
 	}
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(128) at_traceback(const TraceArgs a)
 	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
 	const uint8_t *q = a.q + a.q_off[p], *tg = a.t + a.t_off[p];
 	PtrView pv;
-	pv.R = a.rclass[p]; pv.RPP = 32 * pv.R;
+	pv.R = a.rclass[p] & 15u; pv.RPP = 32 * pv.R; pv.half = (a.rclass[p] >> 4) & 3u;
 	const uint32_t n_stripes = (l1 + pv.RPP - 1) / pv.RPP;
 	const bool jump = a.jump != 0;
 	if (a.mode == MODE_OVERLAP) { const uint32_t tl = steps_last(l2, 15); pv.G = (tl >> 4) + 1; pv.GJ = 0; }

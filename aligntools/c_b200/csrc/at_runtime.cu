@@ -9,6 +9,7 @@
 // entry returns AT_E_CUDA.
 #include "../../../include/aligntools_b200.h"
 #include "at_kernels.cuh"
+#include "at_kernels_p16.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -129,6 +130,9 @@ struct Chunk {
 	std::vector<uint32_t> h_jobs[MAXR + 1];
 	DevBuf<uint32_t> d_jobs[MAXR + 1];
 	uint64_t cells_r[MAXR + 1] = {0};
+	std::vector<uint2> h_jobs2[MAXR + 1];   // packed s16x2 jobs (two pairs per warp)
+	DevBuf<uint2> d_jobs2[MAXR + 1];
+	uint64_t cells_r2[MAXR + 1] = {0};
 	DevBuf<uint64_t> d_ops_off, d_cols_off;
 	DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_aln1, d_aln2;
 	uint64_t tot_ops = 0, tot_cols = 0;
@@ -254,7 +258,7 @@ static void free_shard(Shard &s)
 	s.d_beg_j.release(); s.d_n_ops.release(); s.d_n_cols.release(); s.d_counter.release();
 	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_bnd.release(); s.d_scan_tmp.release();
 	for (auto &c : s.chunks) {
-		c.d_ptr_off.release(); for (auto &j : c.d_jobs) j.release();
+		c.d_ptr_off.release(); for (auto &j : c.d_jobs) j.release(); for (auto &j : c.d_jobs2) j.release();
 		c.d_ops_off.release(); c.d_cols_off.release(); c.d_cigar.release(); c.d_aln1.release(); c.d_aln2.release();
 	}
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
@@ -308,8 +312,6 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		if (l1 > 32u * MAXR) s.multi_stripe = true;
 		s.cells += (uint64_t)l1 * l2;
 	}
-	CU(h, s.d_rclass.alloc(n));
-	CU(h, cudaMemcpyAsync(s.d_rclass.p, s.h_rclass.data(), n, cudaMemcpyHostToDevice, st));
 	CU(h, s.d_score.alloc(n)); CU(h, s.d_end_i.alloc(n)); CU(h, s.d_end_j.alloc(n)); CU(h, s.d_end_state.alloc(n));
 	CU(h, s.d_beg_i.alloc(n)); CU(h, s.d_beg_j.alloc(n)); CU(h, s.d_n_ops.alloc(n + 1)); CU(h, s.d_n_cols.alloc(n + 1));
 	CU(h, cudaMemsetAsync(s.d_n_ops.p, 0, (n + 1) * sizeof(uint32_t), st));
@@ -323,49 +325,96 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, cudaMemGetInfo(&free_b, &total_b));
 	uint64_t budget_words = (uint64_t)(free_b * 0.45) / 4;
 	if (const char *env = getenv("AT_PTR_BUDGET_MB")) budget_words = (uint64_t)atoll(env) * (1ull << 20) / 4;
+	// packed s16x2 lanes (two pairs per warp): local mode, scores x8 must fit int16, m >= u, m-u <= 32
+	const int64_t maxabs = std::max<int64_t>({llabs((long long)b->prm.m), llabs((long long)b->prm.u), llabs((long long)b->prm.o), llabs((long long)b->prm.e), 1});
+	const bool p16_mode = b->mode == AT_LOCAL && b->prm.m >= b->prm.u && b->prm.m - b->prm.u <= 32 && !getenv("AT_NO_P16");
+	auto p16_ok = [&](uint32_t l1, uint32_t l2) {
+		return p16_mode && l1 <= 32u * MAXR && l2 <= 60000u && 8 * (int64_t)(l1 + l2 + 2) * maxabs < 32000;
+	};
 	s.chunks.clear();
 	uint64_t max_chunk_words = 0;
 	{
 		Chunk cur; cur.k0 = 0;
 		uint64_t words = 0;
 		for (uint32_t k = 0; k < n; ++k) {
-			const uint64_t w = b->traceback ? ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]) : 0;
+			const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
+			const uint64_t w = b->traceback ? ptr_words_of(b->mode, jump, l1, l2) + 64ull * rclass_of(l1) : 0;   // + rounding slack of the packed layout
 			if (w > budget_words) { set_err(h, "pair %llu needs %llu MB of traceback pointers; arena budget is %llu MB",
 			                                (unsigned long long)(s.p0 + k), (unsigned long long)(w >> 18), (unsigned long long)(budget_words >> 18)); return AT_E_NOMEM; }
 			if (words + w > budget_words && k > cur.k0) {
-				cur.k1 = k; cur.ptr_words = words; s.chunks.push_back(std::move(cur));
+				cur.k1 = k; s.chunks.push_back(std::move(cur));
 				cur = Chunk(); cur.k0 = k; words = 0;
 			}
-			cur.h_ptr_off.push_back(words);
 			words += w;
 		}
-		cur.k1 = n; cur.ptr_words = words; s.chunks.push_back(std::move(cur));
+		cur.k1 = n; s.chunks.push_back(std::move(cur));
 	}
 	s.ptr_bytes = 0;
 	for (auto &c : s.chunks) {
+		const uint32_t nc = c.k1 - c.k0;
+		auto cells_of = [&](uint32_t k) { return (uint64_t)in->q_len[s.p0 + k] * in->t_len[s.p0 + k]; };
+		// ---- packed jobs: partners must share the rows-per-lane class and l2 ----
+		std::vector<uint32_t> scalar_pairs;
+		{
+			std::vector<uint32_t> cand;
+			for (uint32_t k = c.k0; k < c.k1; ++k) {
+				if (p16_ok(in->q_len[s.p0 + k], in->t_len[s.p0 + k])) cand.push_back(k); else scalar_pairs.push_back(k);
+			}
+			auto key = [&](uint32_t k) { return ((uint64_t)s.h_rclass[k] << 32) | in->t_len[s.p0 + k]; };
+			bool sorted = true;
+			for (size_t x = 1; x < cand.size() && sorted; ++x) sorted = key(cand[x - 1]) >= key(cand[x]);
+			if (!sorted) std::stable_sort(cand.begin(), cand.end(), [&](uint32_t x, uint32_t y) { return key(x) > key(y); });
+			for (size_t x = 0; x < cand.size();) {
+				if (x + 1 < cand.size() && key(cand[x]) == key(cand[x + 1])) {
+					const int r = s.h_rclass[cand[x]] & 15;
+					c.h_jobs2[r].push_back(make_uint2(cand[x], cand[x + 1]));
+					c.cells_r2[r] += cells_of(cand[x]) + cells_of(cand[x + 1]);
+					x += 2;
+				} else { scalar_pairs.push_back(cand[x]); x += 1; }
+			}
+		}
+		// ---- int32 jobs per R class, largest pairs first (dynamic queue => good tail balance) ----
+		{
+			bool ragged = false;
+			for (size_t x = 1; x < scalar_pairs.size() && !ragged; ++x) ragged = cells_of(scalar_pairs[x]) != cells_of(scalar_pairs[0]);
+			if (ragged) std::stable_sort(scalar_pairs.begin(), scalar_pairs.end(), [&](uint32_t x, uint32_t y) { return cells_of(x) > cells_of(y); });
+			for (uint32_t k : scalar_pairs) { const int r = s.h_rclass[k] & 15; c.h_jobs[r].push_back(k); c.cells_r[r] += cells_of(k); }
+		}
+		// ---- pointer blocks: one per int32 pair, one per packed job (shared by its two pairs) ----
+		c.h_ptr_off.assign(nc, 0);
+		uint64_t words = 0;
+		if (b->traceback) {
+			for (int r = 1; r <= MAXR; ++r) {
+				for (uint32_t k : c.h_jobs[r]) { c.h_ptr_off[k - c.k0] = words; words += ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]); }
+				for (const uint2 &jb : c.h_jobs2[r]) {
+					const uint32_t tl = (in->t_len[s.p0 + jb.x] + 31u) | 3u;
+					c.h_ptr_off[jb.x - c.k0] = words; c.h_ptr_off[jb.y - c.k0] = words;
+					s.h_rclass[jb.x] = (uint8_t)(r | (1 << 4)); s.h_rclass[jb.y] = (uint8_t)(r | (2 << 4));
+					words += (uint64_t)((tl >> 2) + 1) * r * 32;
+				}
+			}
+		}
+		c.ptr_words = words;
 		max_chunk_words = std::max(max_chunk_words, c.ptr_words);
 		s.ptr_bytes += c.ptr_words * 4;
-		const uint32_t nc = c.k1 - c.k0;
-		// job lists per R class, largest pairs first (dynamic queue => good tail balance)
-		std::vector<uint32_t> order(nc);
-		for (uint32_t k = 0; k < nc; ++k) order[k] = c.k0 + k;
-		bool ragged = false;
-		const uint64_t c0 = (uint64_t)in->q_len[s.p0 + c.k0] * in->t_len[s.p0 + c.k0];
-		for (uint32_t k = 1; k < nc && !ragged; ++k)
-			ragged = (uint64_t)in->q_len[s.p0 + c.k0 + k] * in->t_len[s.p0 + c.k0 + k] != c0;
-		if (ragged)
-			std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-				return (uint64_t)in->q_len[s.p0 + x] * in->t_len[s.p0 + x] > (uint64_t)in->q_len[s.p0 + y] * in->t_len[s.p0 + y]; });
-		for (uint32_t k : order) { c.h_jobs[s.h_rclass[k]].push_back(k); c.cells_r[s.h_rclass[k]] += (uint64_t)in->q_len[s.p0 + k] * in->t_len[s.p0 + k]; }
-		for (int r = 1; r <= MAXR; ++r) if (!c.h_jobs[r].empty()) {
-			CU(h, c.d_jobs[r].alloc(c.h_jobs[r].size()));
-			CU(h, cudaMemcpyAsync(c.d_jobs[r].p, c.h_jobs[r].data(), c.h_jobs[r].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+		for (int r = 1; r <= MAXR; ++r) {
+			if (!c.h_jobs[r].empty()) {
+				CU(h, c.d_jobs[r].alloc(c.h_jobs[r].size()));
+				CU(h, cudaMemcpyAsync(c.d_jobs[r].p, c.h_jobs[r].data(), c.h_jobs[r].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+			}
+			if (!c.h_jobs2[r].empty()) {
+				CU(h, c.d_jobs2[r].alloc(c.h_jobs2[r].size()));
+				CU(h, cudaMemcpyAsync(c.d_jobs2[r].p, c.h_jobs2[r].data(), c.h_jobs2[r].size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+			}
 		}
 		CU(h, c.d_ptr_off.alloc(nc));
 		CU(h, cudaMemcpyAsync(c.d_ptr_off.p, c.h_ptr_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 		if (b->traceback) { CU(h, c.d_ops_off.alloc(nc + 1)); CU(h, c.d_cols_off.alloc(nc + 1)); }
 		CU(h, cudaStreamSynchronize(st));
 	}
+	CU(h, s.d_rclass.alloc(n));
+	CU(h, cudaMemcpyAsync(s.d_rclass.p, s.h_rclass.data(), n, cudaMemcpyHostToDevice, st));
+	CU(h, cudaStreamSynchronize(st));
 	if (max_chunk_words) {
 		cudaError_t e = s.d_ptr.alloc(max_chunk_words);
 		if (e != cudaSuccess) { set_err(h, "pointer arena of %llu MB: %s", (unsigned long long)(max_chunk_words >> 18), cudaGetErrorString(e)); return AT_E_NOMEM; }
@@ -484,6 +533,37 @@ static cudaError_t fill_launch(int mode, bool jump, int R, const FillArgs &fa, i
 	}
 }
 
+static int p16_occupancy(int R)
+{
+	int nb = 0;
+	switch (R) {
+	case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<1>, 32 * AT_P16_WARPS, 0); break;
+	case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<2>, 32 * AT_P16_WARPS, 0); break;
+	case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<3>, 32 * AT_P16_WARPS, 0); break;
+	case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<4>, 32 * AT_P16_WARPS, 0); break;
+	case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<5>, 32 * AT_P16_WARPS, 0); break;
+	case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<6>, 32 * AT_P16_WARPS, 0); break;
+	case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<7>, 32 * AT_P16_WARPS, 0); break;
+	default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<8>, 32 * AT_P16_WARPS, 0); break;
+	}
+	return nb;
+}
+static cudaError_t p16_launch(int R, const FillArgsP16 &fa, int blocks, cudaStream_t st)
+{
+	const int th = 32 * AT_P16_WARPS;
+	switch (R) {
+	case 1: at_fill_local_p16<1><<<blocks, th, 0, st>>>(fa); break;
+	case 2: at_fill_local_p16<2><<<blocks, th, 0, st>>>(fa); break;
+	case 3: at_fill_local_p16<3><<<blocks, th, 0, st>>>(fa); break;
+	case 4: at_fill_local_p16<4><<<blocks, th, 0, st>>>(fa); break;
+	case 5: at_fill_local_p16<5><<<blocks, th, 0, st>>>(fa); break;
+	case 6: at_fill_local_p16<6><<<blocks, th, 0, st>>>(fa); break;
+	case 7: at_fill_local_p16<7><<<blocks, th, 0, st>>>(fa); break;
+	default: at_fill_local_p16<8><<<blocks, th, 0, st>>>(fa); break;
+	}
+	return cudaGetLastError();
+}
+
 struct CastU64 { __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; } };
 
 static int run_shard(at_batch *b, Shard &s)
@@ -496,7 +576,10 @@ static int run_shard(at_batch *b, Shard &s)
 	// dominant (most cells) fill launch of the whole shard -> per-launch timing for the roofline
 	int dom_chunk = -1, dom_r = -1; uint64_t dom_cells = 0;
 	for (size_t ci = 0; ci < s.chunks.size(); ++ci)
-		for (int r = 1; r <= MAXR; ++r) if (s.chunks[ci].cells_r[r] > dom_cells) { dom_cells = s.chunks[ci].cells_r[r]; dom_chunk = (int)ci; dom_r = r; }
+		for (int r = 1; r <= MAXR; ++r) {
+			if (s.chunks[ci].cells_r[r] > dom_cells) { dom_cells = s.chunks[ci].cells_r[r]; dom_chunk = (int)ci; dom_r = r; }
+			if (s.chunks[ci].cells_r2[r] > dom_cells) { dom_cells = s.chunks[ci].cells_r2[r]; dom_chunk = (int)ci; dom_r = r + 100; }
+		}
 
 	cudaEvent_t e_begin = s.ev[0], e_fill = s.ev[1], e_tb = s.ev[2];
 	float ms = 0;
@@ -516,9 +599,9 @@ static int run_shard(at_batch *b, Shard &s)
 			int blocks = s.dev->sm_count * occ;
 			blocks = (int)std::min<uint64_t>((uint64_t)blocks, (warps_needed + 3) / 4);
 			if (blocks < 1) blocks = 1;
-			if (s.multi_stripe) {
+			if (s.multi_stripe) {     // one boundary slab per resident warp
 				const uint64_t stride = (uint64_t)s.max_l2 + 2;
-				CU(h, s.d_bnd.alloc((size_t)s.dev->sm_count * 16 * 4 * stride > 0 ? (size_t)s.dev->sm_count * 16 * 4 * stride : 1));
+				if (s.d_bnd.alloc((size_t)blocks * 4 * stride) != cudaSuccess) { set_err(h, "stripe boundary slabs"); return AT_E_NOMEM; }
 			} else CU(h, s.d_bnd.alloc(1));
 			FillArgs fa;
 			fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
@@ -529,10 +612,29 @@ static int run_shard(at_batch *b, Shard &s)
 			fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
 			fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
 			fa.want_ptr = b->traceback ? 1 : 0;
-			if (blocks > s.dev->sm_count * 16) blocks = s.dev->sm_count * 16;   // bnd slabs are sized for 16 blocks/SM
 			const bool dom = (int)ci == dom_chunk && r == dom_r;
 			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
 			CU(h, fill_launch(b->mode, jump, r, fa, blocks, st));
+			if (dom) CU(h, cudaEventRecord(s.evk[1], st));
+			s.launches++;
+		}
+		for (int r = 1; r <= MAXR; ++r) {          // packed s16x2 launches (local mode)
+			if (c.h_jobs2[r].empty()) continue;
+			int occ = p16_occupancy(r);
+			if (occ < 1) { set_err(h, "packed fill kernel (R %d) cannot be resident", r); return AT_E_CUDA; }
+			int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (c.h_jobs2[r].size() + AT_P16_WARPS - 1) / AT_P16_WARPS);
+			if (blocks < 1) blocks = 1;
+			FillArgsP16 fa;
+			fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
+			fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
+			fa.jobs = c.d_jobs2[r].p; fa.n_jobs = (uint32_t)c.h_jobs2[r].size();
+			fa.counter = s.d_counter.p + 16 + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
+			fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
+			fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e;
+			fa.want_ptr = b->traceback ? 1 : 0;
+			const bool dom = (int)ci == dom_chunk && r + 100 == dom_r;
+			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
+			CU(h, p16_launch(r, fa, blocks, st));
 			if (dom) CU(h, cudaEventRecord(s.evk[1], st));
 			s.launches++;
 		}

@@ -30,7 +30,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OPS_PER_CELL = {"global": 10, "local": 12, "fit": 10, "fitjump": 14, "overlap": 6, "edit": 6}
-INT32_LANES_PER_SM = 64
+# Integer issue rate MEASURED on this pool's B200 with tools/int_peak.cu (profiles/int_peak_r01.txt):
+# VIMNMX / VIADDMNMX / VIADD.16x2 / LOP3 / IMAD all sustain ~117.6 lane-ops/clk/SM (one warp
+# instruction per scheduler per clock), i.e. 128 nominal lanes, not the 64 SURVEY.md assumed.
+INT32_LANES_PER_SM_MEASURED = 117.6
+NCU_TRAFFIC_BYTES_PER_LAUNCH = None   # dram read+write of one dominant-kernel launch, from profiles/ (ncu --set full)
+PACKED_FACTOR = 2          # one s16x2 instruction advances two cells ("x2 counted for packed s16x2")
 
 
 def env_rank():
@@ -252,7 +257,7 @@ def main():
             if k:
                 e2e_times.append(dt)
             d2h = r2.score.nbytes + 4 * r2.end_i.nbytes + r2.cigar_off.nbytes + int(r2.cigar_off[-1]) * 4
-        e2e_ms = max(e2e_times) if False else sum(e2e_times) / len(e2e_times)
+        e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
         if use_dist:
             tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -265,13 +270,14 @@ def main():
     # ---------------- roofline of the dominant kernel (the local fill) ----------------
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
     k_ms = sum(kern_ms) / len(kern_ms)
-    int_peak = 148 * INT32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12          # T int-op/s, SURVEY.md 8(d)
+    int_peak = 148 * INT32_LANES_PER_SM_MEASURED * PACKED_FACTOR * sm_max_mhz * 1e6 / 1e12     # T int-op/s
     achieved = tm.fill_kernel_cells * OPS_PER_CELL["local"] / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "int32_alu", "achieved": achieved, "peak": int_peak, "unit": "Tiop/s", "frac": achieved / int_peak,
-                "traffic": None, "kernel": "at_fill_affine<LOCAL,R=5>", "kernel_ms": k_ms,
+    roofline = {"bound": "int_alu", "achieved": achieved, "peak": int_peak, "unit": "Tiop/s", "frac": achieved / int_peak,
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "at_fill_local_p16<R=5>", "kernel_ms": k_ms,
                 "kernel_gcups": tm.fill_kernel_cells / (k_ms * 1e-3) / 1e9,
                 "ops_per_cell": OPS_PER_CELL["local"],
-                "peak_note": f"148 SM x {INT32_LANES_PER_SM} int32 lanes x {sm_max_mhz:.0f} MHz (nominal; see DESIGN.md)",
+                "peak_note": (f"148 SM x {INT32_LANES_PER_SM_MEASURED} lane-ops/clk/SM (measured, tools/int_peak.cu) x {PACKED_FACTOR} "
+                              f"(s16x2) x {sm_max_mhz:.0f} MHz; algorithmic ops/cell from SURVEY.md 8(d)"),
                 "hbm": {"bound": "hbm", "achieved": tm.ptr_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": tm.ptr_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "what": "traceback-pointer writes", "peak_src": peak_src}}
 
@@ -287,7 +293,7 @@ def main():
         line = {
             "metric": "GCUPS (fill+traceback, device-timed)", "value": value, "unit": "GCUPS",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16x2", "data": "synthetic",
             "config": {"workload": "C2 batched local SW affine: 150 bp reads vs 500 bp windows (-m 2 -u -2 -o -5 -e -2), score + CIGAR",
                        "pairs_per_gpu": args.pairs, "l1": 150, "l2": 500, "parallelism": f"pairs sharded x{world}, no collective",
                        "l2_policy": "inputs (650 MB sequences + 42 GB pointer arena) are larger than L2"},
