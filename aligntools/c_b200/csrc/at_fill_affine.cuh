@@ -1,0 +1,341 @@
+// at_fill_affine.cuh -- K1: Gotoh M/L/U(/J) fill for global / local / fit (+jump), sm_100a.
+// (included by at_kernels.cuh after FillArgs / constants)
+//
+// One kernel template, two kinds of score lanes:
+//   Lanes<false>  int32   : one pair per warp, any length (reads longer than 32*R rows are cut
+//                           into stripes; lane 31 parks its last row in a boundary slab that
+//                           lane 0 reads back on the next stripe), every mode.
+//   Lanes<true>   s16x2   : TWO pairs per warp, pair A in bits 0-15 and pair B in bits 16-31 of
+//                           every register (VIMNMX.U16x2 / VIADDMNMX.U16x2 DPX instructions);
+//                           local mode, single stripe, both pairs share l2.
+//
+// Geometry: lane k owns R consecutive rows; at step t it works on column j = t - k (anti-diagonal
+// of R-row blocks).  Per step each lane hands the last row of its strip -- M+o, L, H+m and the
+// 2-bit argmax code of H = max(L,M,U[,J]) -- to lane k+1 with four __shfl_up_sync.  Target symbols
+// are staged through a per-warp shared-memory ring (one 32-bit entry per column).
+//
+// Arithmetic (what makes the instruction mix cheap; ncu: the ALU pipe is the binding unit):
+//   * scores are kept x8; a and b being multiples of 8, a != b  =>  |a-b| >= 8, so a traceback
+//     flag is  min(max(a,b) - b, 1|3|4|8)  : one subtract (FMA-pipe IMAD.IADD) + one VIMNMX, and
+//     it lands on its bit of the pointer nibble without shifts;
+//   * packed lanes are BIASED by 0x8000 per half and compared unsigned, so every add/subtract is
+//     an ordinary 32-bit integer instruction (no carry can cross the halves while the values
+//     stay in range, which the host checks) and can be issued on the FMA pipe;
+//   * symbols are pre-shifted (<<8 / <<16), so  min(a ^ b, 8|m-u|)  is 0 on a match and the
+//     whole substitution penalty otherwise;  M = (H+m) - that;
+//   * local mode keeps the lane's running maximum of  8*M + (7 - row_in_lane)  with one
+//     VIADDMNMX per cell: larger score first, then the smaller row -- together with "first step
+//     at which the key reached its final value" this is the reference's first maximum in
+//     row-major order (src/alignment.h:830-833).
+//
+// Reference recurrences: src/alignment.h:451-462 (global), :635-667 (fit), :825-841 (local);
+// tie rules SURVEY.md A.0:  M: first strictly greater in order L,M,U,(J|HOME);  L: extend wins
+// ties;  U: open wins ties;  J: enter wins ties, entering forbidden on listed target indices.
+#pragma once
+
+namespace at {
+
+#define AT_RING 512        // target ring entries per warp (two 256-column blocks)
+#define AT_FILL_WARPS 4
+
+template <bool PACKED> struct Lanes;
+
+template <> struct Lanes<false> {
+	typedef int32_t T;
+	static constexpr int CSHIFT = 16;
+	static constexpr uint32_t STEPS_PER_WORD = 8;
+	__device__ __forceinline__ static T vmax(T a, T b) { return max(a, b); }
+	__device__ __forceinline__ static T flag(T d, uint32_t k) { return (T)min((uint32_t)d, k); }     // d >= 0
+	__device__ __forceinline__ static T addmax(T a, T b, T c) { return __viaddmax_s32(a, b, c); }
+	__device__ __forceinline__ static T delta(int v) { return 8 * v; }
+	__device__ __forceinline__ static T delta_h(int v) { return 8 * v; }
+	__device__ __forceinline__ static T value(int v) { return 8 * v; }
+	__device__ __forceinline__ static T raw(int v) { return v; }
+};
+
+template <> struct Lanes<true> {
+	typedef uint32_t T;
+	static constexpr int CSHIFT = 8;
+	static constexpr uint32_t STEPS_PER_WORD = 4;
+	__device__ __forceinline__ static T vmax(T a, T b) { return __vmaxu2(a, b); }
+	__device__ __forceinline__ static T flag(T d, uint32_t k) { return __vminu2(d, k * 0x10001u); }
+	__device__ __forceinline__ static T addmax(T a, T b, T c) { return __viaddmax_u16x2(a, b, c); }
+	__device__ __forceinline__ static T delta(int v) { return (uint32_t)(8 * v * 0x10001); }           // exact 32-bit sum of both halves: for IADD/IMAD
+	__device__ __forceinline__ static T delta_h(int v) { return ((uint32_t)(8 * v) & 0xffffu) * 0x10001u; } // two's complement per half: for VIADDMNMX.U16x2
+	__device__ __forceinline__ static T value(int v) { return (uint32_t)(8 * v * 0x10001) + 0x80008000u; }
+	__device__ __forceinline__ static T raw(int v) { return (uint32_t)(v * 0x10001); }
+};
+
+struct FillJob { uint32_t a, b; };     // pair indices; b == a for int32 lanes or a packed job without partner
+
+struct FillArgs2 {
+	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
+	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
+	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
+	const FillJob  *jobs;
+	uint32_t        n_jobs;
+	uint32_t       *counter;
+	uint32_t       *ptr;     const uint64_t *ptr_off;   uint32_t pair_base;
+	int4           *bnd;     uint32_t bnd_stride;
+	int32_t        *score;   uint32_t *end_i;  uint32_t *end_j;  uint8_t *end_state;
+	int             m, u, o, e, jp;
+	int             want_ptr;
+};
+
+template <int MODE, int R, bool JUMP, bool PACKED, bool MULTI>
+__global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillArgs2 a)
+{
+	typedef Lanes<PACKED> V;
+	typedef typename V::T T;
+	static_assert(!PACKED || (MODE == MODE_LOCAL && !JUMP && !MULTI), "packed lanes: local, single stripe");
+	constexpr uint32_t SPW = V::STEPS_PER_WORD;
+	constexpr int RPP = 32 * R;
+
+	__shared__ uint32_t ring_all[AT_FILL_WARPS][AT_RING];
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t *ring = ring_all[threadIdx.x >> 5];
+
+	const int m = a.m, u = a.u, o = a.o, e = a.e;
+	const T m8 = V::delta(m), o8 = V::delta(o), e8 = V::delta(e), e8h = V::delta_h(e);
+	const uint32_t mu8 = (uint32_t)(8 * (m >= u ? m - u : u - m));     // per half; < 1 << CSHIFT (host-checked)
+	const int nsg = m >= u ? -1 : 1;                                    // M = (H+m) - penalty  (or + when u > m)
+	const T ZERO = V::value(0);
+	const T NEGV = PACKED ? ZERO : (T)AT_NEG;                           // -inf stand-in (int32 lanes only)
+	const bool want_ptr = a.want_ptr != 0;
+
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0) job = atomicAdd(a.counter, 1u);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= a.n_jobs) break;
+		const FillJob jb = a.jobs[job];
+		const uint32_t pA = jb.a, pB = PACKED ? jb.b : jb.a;
+		const uint32_t l1A = a.q_len[pA], l1B = a.q_len[pB], l2 = a.t_len[pA];
+		const uint8_t *__restrict__ qA = a.q + a.q_off[pA], *__restrict__ qB = a.q + a.q_off[pB];
+		const uint8_t *__restrict__ tA = a.t + a.t_off[pA], *__restrict__ tB = a.t + a.t_off[pB];
+		const uint8_t *__restrict__ jm = JUMP ? a.jmask + a.t_off[pA] : nullptr;
+		uint32_t *__restrict__ ptr = a.ptr + a.ptr_off[pA - a.pair_base];
+		const uint32_t t_last = (l2 + 31u) | (JUMP ? 31u : (SPW - 1u));
+		const uint32_t G = t_last / SPW + 1, GJ = (t_last >> 5) + 1;
+		const uint32_t n_stripes = MULTI ? (l1A + RPP - 1) / RPP : 1;
+		uint32_t *__restrict__ ptrJ = ptr + (size_t)n_stripes * G * RPP;
+		int4 *__restrict__ bnd = MULTI ? a.bnd + (size_t)warp_slot * a.bnd_stride : nullptr;
+
+		// ring[(j-1) & 511]: packed (tA << 8) | (tB << 24); int32 (tA << 16) | blacklist bit
+		auto load_block = [&](uint32_t blk) {
+			const uint32_t base = blk * 256u;
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const uint32_t idx = base + k * 32u + lane;
+				uint32_t v = PACKED ? 0x00010001u : 0x2u;      // past the end: never equals a symbol
+				if (idx < l2) {
+					if (PACKED) v = ((uint32_t)__ldg(tA + idx) << 8) | ((uint32_t)__ldg(tB + idx) << 24);
+					else { v = (uint32_t)__ldg(tA + idx) << 16; if (JUMP) v |= __ldg(jm + idx) ? 1u : 0u; }
+				}
+				ring[idx & (AT_RING - 1)] = v;
+			}
+		};
+
+		// results
+		int lbest_sc[2] = {-1, -1}, lbest_i[2] = {0x7fffffff, 0x7fffffff}, lbest_j[2] = {0, 0};   // local
+		int capM = AT_NEG_INIT, capMj = 0, capL = AT_NEG_INIT, capLj = 0;                     // fit
+		int gH = 0, gC = 0;                                                                    // global
+
+		for (uint32_t stripe = 0; stripe < n_stripes; ++stripe) {
+			const uint32_t row0 = stripe * RPP + lane * R;
+			const bool last_stripe = stripe + 1 == n_stripes;
+			__syncwarp();
+			load_block(0);
+			load_block(1);
+			__syncwarp();
+
+			T Mol[R], Ul[R], Hl[R], Cl[R], Jl[R], crow[R];
+			uint32_t ac[R], acc[R], accJ[R];
+#pragma unroll
+			for (int r = 0; r < R; ++r) {
+				const uint32_t ri = row0 + r;
+				const int i = (int)ri + 1;
+				if (PACKED) {
+					const uint32_t ca = ri < l1A ? ((uint32_t)qA[ri] << 8) : 0x0002u;
+					const uint32_t cb = ri < l1B ? ((uint32_t)qB[ri] << 8) : 0x0002u;
+					ac[r] = ca | (cb << 16);
+					// running-max key offset: 7 - r for real rows; -0x8000 sinks padded rows below every real key
+					crow[r] = (T)((ri < l1A ? (uint32_t)(7 - r) : 0x8000u) | ((ri < l1B ? (uint32_t)(7 - r) : 0x8000u) << 16));
+				} else {
+					ac[r] = ri < l1A ? ((uint32_t)qA[ri] << 16) : 0x4u;
+					crow[r] = (T)(ri < l1A ? 7 - r : -(1 << 28));
+				}
+				// column 0 (left border)
+				if (MODE == MODE_GLOBAL)     { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = V::value(o + e * i) + m8; Cl[r] = V::raw(ST_LOW); }   // :432-436
+				else if (MODE == MODE_LOCAL) { Mol[r] = ZERO + o8; Ul[r] = ZERO; Hl[r] = ZERO + m8; Cl[r] = V::raw(ST_LOW); }             // calloc zeros
+				else                         { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = NEGV; Cl[r] = V::raw(ST_MID); }                       // :612-617
+				Jl[r] = NEGV; acc[r] = 0; accJ[r] = 0;
+			}
+			T sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
+			T sL = MODE == MODE_GLOBAL ? V::value(o + e * (int)(row0 + R)) : (MODE == MODE_LOCAL ? ZERO : NEGV);
+			T pH, pC;      // H(row0, 0) + m and its code
+			if (row0 == 0) {
+				if (MODE == MODE_GLOBAL)     { pH = V::value(o < 0 ? 0 : o) + m8; pC = V::raw(o < 0 ? ST_MID : ST_LOW); }   // max5(L=o, M=0, U=o)
+				else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = V::raw(ST_LOW); }
+				else                         { pH = ZERO + m8; pC = V::raw(ST_MID); }                                       // M[0][0]=U[0][0]=0
+			} else {
+				if (MODE == MODE_GLOBAL)     { pH = V::value(o + e * (int)row0) + m8; pC = V::raw(ST_LOW); }
+				else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = V::raw(ST_LOW); }
+				else                         { pH = NEGV; pC = V::raw(ST_MID); }
+			}
+			const int cap_r = (!PACKED && last_stripe && lane == (int)(((l1A - 1) % RPP) / R)) ? (int)((l1A - 1) % R) : -1;
+			T kbest = PACKED ? (T)0 : (T)AT_NEG_INIT;     // below every real key
+			T tbest = 0;
+			int4 top_next = make_int4(0, 0, 0, 0);
+			if (MULTI && stripe > 0 && lane == 0) top_next = bnd[1];
+
+			auto step = [&](const uint32_t t, const bool checked) {
+				const int j = (int)t - lane;
+				T rM = __shfl_up_sync(0xffffffffu, sM, 1);
+				T rL = __shfl_up_sync(0xffffffffu, sL, 1);
+				T rH = __shfl_up_sync(0xffffffffu, sH, 1);
+				T rC = __shfl_up_sync(0xffffffffu, sC, 1);
+				if (lane == 0) {
+					if (!MULTI || stripe == 0) {     // matrix row 0 at column j = t
+						if (MODE == MODE_GLOBAL)     { rM = NEGV; rL = NEGV; rH = V::value(o + e * j) + m8; rC = V::raw(ST_UPP); }   // :437-441
+						else if (MODE == MODE_LOCAL) { rM = ZERO + o8; rL = ZERO; rH = ZERO + m8; rC = V::raw(ST_LOW); }
+						else                         { rM = ZERO + o8; rL = NEGV; rH = ZERO + m8; rC = V::raw(ST_MID); }             // :619-624
+					} else {
+						rM = (T)top_next.x; rL = (T)top_next.y; rH = (T)top_next.z; rC = (T)top_next.w;
+						if (t + 1 <= l2) top_next = bnd[t + 1];
+					}
+				}
+				if (checked && t == 0) { rH = pH; rC = pC; }   // step 0 only primes the pipeline: keep H(row0, 0)
+				T D = pH, DC = pC;
+				pH = rH; pC = rC;
+				if (!checked || (j >= 1 && j <= (int)l2)) {
+					uint32_t c = ring[(uint32_t)(j - 1) & (AT_RING - 1)];
+					T jadd = 0;
+					if (JUMP) { jadd = (c & 1u) ? (T)AT_NEG : V::delta(a.jp - o); c &= ~1u; }   // M[i][j-1] + jump, or barred (:659-665)
+					T Lup = rL, MoUp = rM, Mo = 0, Ln = 0, Hm = 0, code = 0;
+					const T kold = kbest;
+#pragma unroll
+					for (int r = 0; r < R; ++r) {
+						const T tt = V::flag((T)(ac[r] ^ c), mu8);              // 0 on a match, 8|m-u| otherwise
+						const T Mraw = tt * (T)nsg + D;                         // H(i-1,j-1) + s
+						T Mn = Mraw, pm = DC;
+						if (MODE == MODE_LOCAL) { Mn = V::vmax(Mraw, ZERO); pm = DC | V::flag(Mn - Mraw, 3); }   // HOME: 0.0 strictly greater (:825)
+						const T Lext = Lup + e8;
+						Ln = V::vmax(Lext, MoUp);
+						const T fL = V::flag(Ln - Lext, 4);                     // gap opened only when strictly better (:456)
+						const T Un = V::addmax(Ul[r], e8h, Mol[r]);
+						const T fU = V::flag(Un - Mol[r], 8);                   // gap extended only when strictly better (:460)
+						T Jn = 0, fJ = 0;
+						if (JUMP) {
+							const T ent = Mol[r] + jadd;
+							Jn = V::vmax(ent, Jl[r]);
+							fJ = V::flag(Jn - ent, 1);                          // stay in J only when strictly better (:660)
+						}
+						Mo = Mn + o8;
+						const T t1 = V::vmax(Ln, Mn);
+						T H = V::vmax(t1, Un);
+						code = V::flag(H - Ln, 1) + V::flag(H - t1, 1);         // 0 LOW, 1 MID, 2 UPP: first strictly greater, order L,M,U
+						if (JUMP) { const T H4 = V::vmax(H, Jn); code = V::vmax(code, V::flag(H4 - H, 3)); H = H4; }
+						Hm = H + m8;
+						acc[r] = acc[r] * 16u + (uint32_t)(pm | fL) + (uint32_t)fU;
+						if (JUMP) accJ[r] = accJ[r] * 2u + (uint32_t)fJ;
+						if (MODE == MODE_LOCAL) kbest = V::addmax(Mn, crow[r], kbest);
+						if (MODE == MODE_FIT) {
+							if (r == cap_r && j < (int)l2) {                   // column l2 excluded (:677, :684)
+								if ((int)Mn > capM) { capM = (int)Mn; capMj = j; }
+								if ((int)Ln > capL) { capL = (int)Ln; capLj = j; }
+							}
+						}
+						if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) { gH = (int)H; gC = (int)code; } }
+						D = Hl[r]; DC = Cl[r];
+						Hl[r] = Hm; Cl[r] = code; Ul[r] = Un; Mol[r] = Mo; if (JUMP) Jl[r] = Jn;
+						Lup = Ln; MoUp = Mo;
+					}
+					sM = Mo; sL = Ln; sH = Hm; sC = code;
+					if (MODE == MODE_LOCAL) {     // first step at which the running key took its (so far) final value
+						if (PACKED) { const T chg = V::flag(kbest ^ kold, 1) * 0xffffu; tbest = (tbest & ~chg) | ((T)(t * 0x10001u) & chg); }
+						else if (kbest != kold) tbest = (T)t;
+					}
+					if (MULTI) { if (lane == 31 && !last_stripe) bnd[j] = make_int4((int)sM, (int)sL, (int)sH, (int)sC); }
+				} else {
+#pragma unroll
+					for (int r = 0; r < R; ++r) { acc[r] *= 16u; if (JUMP) accJ[r] *= 2u; }
+				}
+			};
+
+			for (uint32_t tb = 0; tb <= t_last; tb += SPW) {
+				if ((tb & 255u) == 32u && tb > 32u) {     // block tb/256 - 1 is dead: refill its slots two blocks ahead
+					__syncwarp();
+					load_block(tb / 256u + 1u);
+					__syncwarp();
+				}
+				if (tb >= 32u && tb + SPW - 1u <= l2) {
+#pragma unroll
+					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false);
+				} else {
+#pragma unroll
+					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true);
+				}
+				if (want_ptr) {
+					uint32_t *w = ptr + ((size_t)(stripe * G + tb / SPW) * R) * 32 + lane;
+#pragma unroll
+					for (int r = 0; r < R; ++r) w[r * 32] = acc[r];
+				}
+				if (PACKED) {
+#pragma unroll
+					for (int r = 0; r < R; ++r) acc[r] = 0;   // 4 nibbles per half: the next shift must not spill A's bits into B's half
+				}
+				if (JUMP && want_ptr && ((tb + SPW - 1u) & 31u) == 31u) {
+					uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (tb >> 5)) * R) * 32 + lane;
+#pragma unroll
+					for (int r = 0; r < R; ++r) w[r * 32] = accJ[r];
+				}
+			}
+
+			if (MODE == MODE_LOCAL) {   // fold this stripe's lane maximum into (score, row, column) per pair half
+#pragma unroll
+				for (int h = 0; h < (PACKED ? 2 : 1); ++h) {
+					int key, tcol;
+					if (PACKED) { key = (int)((kbest >> (16 * h)) & 0xffffu) - 0x8000; tcol = (int)((tbest >> (16 * h)) & 0xffffu) - lane; }
+					else { key = (int)kbest; tcol = (int)tbest - lane; }
+					const bool real = key >= 0;
+					if (real) {
+						const int sc = key >> 3, row = (int)row0 + (7 - (key & 7)) + 1;
+						if (sc > lbest_sc[h]) { lbest_sc[h] = sc; lbest_i[h] = row; lbest_j[h] = tcol; }   // later stripes hold larger rows: strict >
+					}
+				}
+			}
+			__syncwarp();
+		}
+
+		// ---- end cell (reference: :466-469 global, :673-690 fit, running max :830-833 local) ----
+		if (MODE == MODE_LOCAL) {
+#pragma unroll
+			for (int h = 0; h < (PACKED ? 2 : 1); ++h) {
+				int sc = lbest_sc[h], row = lbest_i[h], col = lbest_j[h];
+#pragma unroll
+				for (int d = 16; d >= 1; d >>= 1) {
+					const int osc = __shfl_xor_sync(0xffffffffu, sc, d);
+					const int orow = __shfl_xor_sync(0xffffffffu, row, d);
+					const int ocol = __shfl_xor_sync(0xffffffffu, col, d);
+					if (osc > sc || (osc == sc && orow < row)) { sc = osc; row = orow; col = ocol; }
+				}
+				const uint32_t p = h ? pB : pA;
+				if (lane == 0 && (h == 0 || pB != pA)) { a.score[p] = sc; a.end_i[p] = row; a.end_j[p] = col; a.end_state[p] = ST_MID; }
+			}
+		} else {
+			const int owner = (int)(((l1A - 1) % RPP) / R);
+			if (lane == owner) {
+				if (MODE == MODE_GLOBAL) { a.score[pA] = gH >> 3; a.end_i[pA] = l1A; a.end_j[pA] = l2; a.end_state[pA] = (uint8_t)gC; }
+				else {
+					const bool useL = capL > capM;            // L replaces M only when strictly greater (:685)
+					a.score[pA] = (useL ? capL : capM) >> 3; a.end_i[pA] = l1A; a.end_j[pA] = useL ? capLj : capMj;
+					a.end_state[pA] = useL ? ST_LOW : ST_MID;
+				}
+			}
+		}
+	}
+}
+
+}  // namespace at

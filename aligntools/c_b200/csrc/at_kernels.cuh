@@ -39,7 +39,7 @@ struct FillArgs {
 	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
 	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
 	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
-	const uint32_t *jobs;    // pair indices handled by this launch (largest first)
+	const uint32_t *jobs;    // FillJob records {a, b} (largest pairs first); the single-plane kernels read .a
 	uint32_t        n_jobs;
 	uint32_t       *counter; // dynamic job queue
 	uint32_t       *ptr;     // traceback pointer arena (32-bit words)
@@ -54,195 +54,9 @@ struct FillArgs {
 
 __device__ __forceinline__ uint32_t steps_last(uint32_t l2, int align_mask) { return (l2 + 31u) | (uint32_t)align_mask; }
 
-// ------------------------------------------------------------------------------------
-// Affine fill.  Per cell (reference recurrences src/alignment.h:451-462 global, :635-667
-// fit, :825-841 local; tie rules SURVEY.md A.0):
-//   M = max5(L'+s, M'+s, U'+s, X)   first strictly greater wins, order L,M,U,(J|HOME)
-//   L = max(L^+e, M^+o)             extend wins ties     (^ = cell above)
-//   U = max(M<+o, U<+e)             open wins ties       (< = cell to the left)
-//   J = max(M<+j, J<)  or  J<       enter wins ties; entering forbidden on listed columns
-// H = max(L,M,U[,J]) and its argmax code are produced where the cell is computed and
-// consumed by the diagonal neighbour, so pointerM(i,j) == code(i-1,j-1) unless HOME wins.
-// ------------------------------------------------------------------------------------
-template <int MODE, int R, bool JUMP>
-__device__ __forceinline__ void fill_affine_pair(const FillArgs &a, const uint32_t p, const int lane, const uint32_t warp_slot)
-{
-	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
-	const uint8_t *__restrict__ q  = a.q + a.q_off[p];
-	const uint8_t *__restrict__ tg = a.t + a.t_off[p];
-	const uint8_t *__restrict__ jm = JUMP ? a.jmask + a.t_off[p] : nullptr;
-	uint32_t *__restrict__ ptr = a.ptr + a.ptr_off[p - a.pair_base];
-	const int m = a.m, u = a.u, o = a.o, e = a.e, jpo = a.jp - a.o;
-	constexpr int RPP = 32 * R;                       // rows per stripe
-	const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
-	const uint32_t t_last = steps_last(l2, JUMP ? 31 : 7);
-	const uint32_t G = (t_last >> 3) + 1, GJ = (t_last >> 5) + 1;
-	uint32_t *__restrict__ ptrJ = ptr + (size_t)n_stripes * G * RPP;   // J bit-plane follows the nibble plane
-	int4 *__restrict__ bnd = a.bnd + (size_t)warp_slot * a.bnd_stride;
-	const bool want_ptr = a.want_ptr != 0;
-
-	int lbest = AT_NEG_INIT, lbi = 0, lbj = 0;                 // local: first maximum in row-major order
-	int capM = AT_NEG_INIT, capMj = 0, capL = AT_NEG_INIT, capLj = 0;   // fit: last-row search
-	int gH = 0, gC = 0;                                       // global: cell (l1,l2)
-
-	for (uint32_t stripe = 0; stripe < n_stripes; ++stripe) {
-		const uint32_t row0 = stripe * RPP + lane * R;        // matrix row above the lane's strip
-		const bool last_stripe = stripe + 1 == n_stripes;
-		int ac[R], Mol[R], Ul[R], Hl[R], Cl[R], Jl[R], best[R], bj[R];
-		uint32_t acc[R], accJ[R];
-#pragma unroll
-		for (int r = 0; r < R; ++r) {
-			const uint32_t ri = row0 + r;                     // 0-based read index; matrix row i = ri+1
-			ac[r] = ri < l1 ? (int)q[ri] : 0x100;
-			const int i = (int)ri + 1;
-			if (MODE == MODE_GLOBAL)      { Mol[r] = AT_NEG; Ul[r] = AT_NEG; Hl[r] = o + e * i; Cl[r] = ST_LOW; }   // :432-436
-			else if (MODE == MODE_LOCAL)  { Mol[r] = o;      Ul[r] = 0;      Hl[r] = 0;         Cl[r] = ST_LOW; }   // calloc zeros
-			else                          { Mol[r] = AT_NEG; Ul[r] = AT_NEG; Hl[r] = AT_NEG;    Cl[r] = ST_MID; }   // :612-617
-			Jl[r] = AT_NEG; acc[r] = 0; accJ[r] = 0;
-			best[r] = ri < l1 ? AT_NEG_INIT : 0x7fffffff; bj[r] = 0;
-		}
-		// what this lane hands to lane+1 before it becomes active: column 0 of its last row
-		int sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
-		int sL = MODE == MODE_GLOBAL ? o + e * (int)(row0 + R) : (MODE == MODE_LOCAL ? 0 : AT_NEG);
-		// diagonal input of the first row at column 1: H(row0, 0)
-		int pH, pC;
-		if (row0 == 0) {
-			if (MODE == MODE_GLOBAL)     { pH = o < 0 ? 0 : o; pC = o < 0 ? ST_MID : ST_LOW; }   // max5(L=o, M=0, U=o)
-			else if (MODE == MODE_LOCAL) { pH = 0; pC = ST_LOW; }
-			else                         { pH = 0; pC = ST_MID; }                                // M[0][0]=U[0][0]=0, L=-inf
-		} else {
-			if (MODE == MODE_GLOBAL)     { pH = o + e * (int)row0; pC = ST_LOW; }
-			else if (MODE == MODE_LOCAL) { pH = 0; pC = ST_LOW; }
-			else                         { pH = AT_NEG; pC = ST_MID; }
-		}
-		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
-		int4 top_next = make_int4(0, 0, 0, 0);
-		if (stripe > 0 && lane == 0) top_next = bnd[1];
-
-		for (uint32_t t = 1; t <= t_last; ++t) {
-			const int j = (int)t - lane;
-			int rM = __shfl_up_sync(0xffffffffu, sM, 1);
-			int rL = __shfl_up_sync(0xffffffffu, sL, 1);
-			int rH = __shfl_up_sync(0xffffffffu, sH, 1);
-			int rC = __shfl_up_sync(0xffffffffu, sC, 1);
-			if (lane == 0) {
-				if (stripe == 0) {    // matrix row 0 at column j = t
-					if (MODE == MODE_GLOBAL)     { rM = AT_NEG; rL = AT_NEG; rH = o + e * j; rC = ST_UPP; }   // :437-441
-					else if (MODE == MODE_LOCAL) { rM = o;      rL = 0;      rH = 0;         rC = ST_LOW; }
-					else                         { rM = o;      rL = AT_NEG; rH = 0;         rC = ST_MID; }   // :619-624
-				} else {
-					rM = top_next.x; rL = top_next.y; rH = top_next.z; rC = top_next.w;
-					if (t + 1 <= l2) top_next = bnd[t + 1];
-				}
-			}
-			int D = pH, DC = pC;
-			pH = rH; pC = rC;
-			if (j >= 1 && j <= (int)l2) {
-				const int c = (int)__ldg(tg + (j - 1));
-				bool allowed = false;
-				if (JUMP) allowed = __ldg(jm + (j - 1)) == 0;
-				int Lup = rL, MoUp = rM;
-				int Mo = 0, Ln = 0, H = 0, code = 0;
-#pragma unroll
-				for (int r = 0; r < R; ++r) {
-					const int s = (ac[r] == c) ? m : u;
-					const int Mraw = D + s;
-					int pm = DC, Mn = Mraw;
-					if (MODE == MODE_LOCAL) { if (Mraw < 0) pm = 3; Mn = max(Mraw, 0); }    // HOME: 0.0 strictly greater (:825)
-					const int Lext = Lup + e;
-					const bool fL = MoUp > Lext;            // gap opened (MID) only when strictly better (:456)
-					Ln = max(Lext, MoUp);
-					const int Uext = Ul[r] + e;
-					const bool fU = Uext > Mol[r];          // gap extended (UPP) only when strictly better (:460)
-					const int Un = max(Uext, Mol[r]);
-					int Jn = AT_NEG; bool fJ = false;
-					if (JUMP) {
-						const int ent = allowed ? Mol[r] + jpo : AT_NEG;    // M[i][j-1] + jump (:660)
-						fJ = Jl[r] > ent;                   // stay in J only when strictly better
-						Jn = max(ent, Jl[r]);
-					}
-					Mo = Mn + o;
-					const int t1 = max(Ln, Mn);
-					H = max(t1, Un);
-					code = (H != Ln) + (H != t1);           // 0 LOW, 1 MID, 2 UPP: first strictly greater in order L,M,U
-					if (JUMP) { if (Jn > H) code = ST_JUMP; H = max(H, Jn); }
-					const uint32_t nib = (uint32_t)pm | (fL ? 4u : 0u) | (fU ? 8u : 0u);
-					acc[r] = (acc[r] << 4) | nib;
-					if (JUMP) accJ[r] = (accJ[r] << 1) | (fJ ? 1u : 0u);
-					if (MODE == MODE_LOCAL) { if (Mn > best[r]) { best[r] = Mn; bj[r] = j; } }   // :830-833
-					if (MODE == MODE_FIT) {
-						if (r == cap_r && j < (int)l2) {     // column l2 excluded (:677, :684)
-							if (Mn > capM) { capM = Mn; capMj = j; }
-							if (Ln > capL) { capL = Ln; capLj = j; }
-						}
-					}
-					if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) { gH = H; gC = code; } }
-					// roll the per-row state
-					D = Hl[r]; DC = Cl[r];
-					Hl[r] = H; Cl[r] = code; Ul[r] = Un; Mol[r] = Mo; if (JUMP) Jl[r] = Jn;
-					Lup = Ln; MoUp = Mo;
-				}
-				sM = Mo; sL = Ln; sH = H; sC = code;
-				if (lane == 31 && !last_stripe) bnd[j] = make_int4(sM, sL, sH, sC);
-			} else {
-#pragma unroll
-				for (int r = 0; r < R; ++r) { acc[r] <<= 4; if (JUMP) accJ[r] <<= 1; }
-			}
-			if ((t & 7u) == 7u && want_ptr) {
-				uint32_t *w = ptr + ((size_t)(stripe * G + (t >> 3)) * R) * 32 + lane;
-#pragma unroll
-				for (int r = 0; r < R; ++r) w[r * 32] = acc[r];
-			}
-			if (JUMP && (t & 31u) == 31u && want_ptr) {
-				uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (t >> 5)) * R) * 32 + lane;
-#pragma unroll
-				for (int r = 0; r < R; ++r) w[r * 32] = accJ[r];
-			}
-		}
-		if (MODE == MODE_LOCAL) {
-#pragma unroll
-			for (int r = 0; r < R; ++r)
-				if (best[r] != 0x7fffffff && best[r] > lbest) { lbest = best[r]; lbi = (int)(row0 + r) + 1; lbj = bj[r]; }
-		}
-		__syncwarp();
-	}
-
-	// ---- end cell (reference: :466-469 global, :673-690 fit, running max :830-833 local) ----
-	if (MODE == MODE_LOCAL) {
-#pragma unroll
-		for (int d = 16; d >= 1; d >>= 1) {
-			const int ov = __shfl_xor_sync(0xffffffffu, lbest, d);
-			const int oi = __shfl_xor_sync(0xffffffffu, lbi, d);
-			const int oj = __shfl_xor_sync(0xffffffffu, lbj, d);
-			if (ov > lbest || (ov == lbest && oi < lbi)) { lbest = ov; lbi = oi; lbj = oj; }
-		}
-		if (lane == 0) { a.score[p] = lbest; a.end_i[p] = lbi; a.end_j[p] = lbj; a.end_state[p] = ST_MID; }
-	} else {
-		const int owner = (int)(((l1 - 1) % RPP) / R);
-		if (lane == owner) {
-			if (MODE == MODE_GLOBAL) { a.score[p] = gH; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = (uint8_t)gC; }
-			else {
-				const bool useL = capL > capM;            // L replaces M only when strictly greater (:685)
-				a.score[p] = useL ? capL : capM; a.end_i[p] = l1; a.end_j[p] = useL ? capLj : capMj;
-				a.end_state[p] = useL ? ST_LOW : ST_MID;
-			}
-		}
-	}
-}
-
-template <int MODE, int R, bool JUMP>
-__global__ void __launch_bounds__(128) at_fill_affine(const FillArgs a)
-{
-	const int lane = threadIdx.x & 31;
-	const uint32_t warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	for (;;) {
-		uint32_t job = 0;
-		if (lane == 0) job = atomicAdd(a.counter, 1u);
-		job = __shfl_sync(0xffffffffu, job, 0);
-		if (job >= a.n_jobs) break;
-		fill_affine_pair<MODE, R, JUMP>(a, a.jobs[job], lane, warp_slot);
-	}
-}
+}  // namespace at
+#include "at_fill_affine.cuh"
+namespace at {
 
 // ------------------------------------------------------------------------------------
 // Single-plane fill: overlap (src/alignment.h:926-964, linear gap `o`, order
@@ -344,7 +158,7 @@ __global__ void __launch_bounds__(128) at_fill_linear(const FillArgs a)
 		if (lane == 0) job = atomicAdd(a.counter, 1u);
 		job = __shfl_sync(0xffffffffu, job, 0);
 		if (job >= a.n_jobs) break;
-		fill_linear_pair<MODE, R>(a, a.jobs[job], lane, warp_slot);
+		fill_linear_pair<MODE, R>(a, a.jobs[2 * job], lane, warp_slot);   // jobs are FillJob{a,b} records; int32 lanes use .a
 	}
 }
 

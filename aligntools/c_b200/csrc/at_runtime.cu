@@ -9,7 +9,6 @@
 // entry returns AT_E_CUDA.
 #include "../../../include/aligntools_b200.h"
 #include "at_kernels.cuh"
-#include "at_kernels_p16.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -127,11 +126,12 @@ struct Chunk {
 	uint64_t ptr_words = 0;
 	std::vector<uint64_t> h_ptr_off;    // chunk-local
 	DevBuf<uint64_t> d_ptr_off;
-	std::vector<uint32_t> h_jobs[MAXR + 1];
-	DevBuf<uint32_t> d_jobs[MAXR + 1];
+	std::vector<FillJob> h_jobs[MAXR + 1];  // int32 lanes: one pair per warp (a == b)
+	DevBuf<FillJob> d_jobs[MAXR + 1];
+	bool multi_r[MAXR + 1] = {false};
 	uint64_t cells_r[MAXR + 1] = {0};
-	std::vector<uint2> h_jobs2[MAXR + 1];   // packed s16x2 jobs (two pairs per warp)
-	DevBuf<uint2> d_jobs2[MAXR + 1];
+	std::vector<FillJob> h_jobs2[MAXR + 1]; // packed s16x2 lanes: two pairs per warp
+	DevBuf<FillJob> d_jobs2[MAXR + 1];
 	uint64_t cells_r2[MAXR + 1] = {0};
 	DevBuf<uint64_t> d_ops_off, d_cols_off;
 	DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_aln1, d_aln2;
@@ -325,9 +325,9 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, cudaMemGetInfo(&free_b, &total_b));
 	uint64_t budget_words = (uint64_t)(free_b * 0.45) / 4;
 	if (const char *env = getenv("AT_PTR_BUDGET_MB")) budget_words = (uint64_t)atoll(env) * (1ull << 20) / 4;
-	// packed s16x2 lanes (two pairs per warp): local mode, scores x8 must fit int16, m >= u, m-u <= 32
+	// packed s16x2 lanes (two pairs per warp): local mode, scores x8 must fit int16, 8|m-u| < 256 (symbols are << 8)
 	const int64_t maxabs = std::max<int64_t>({llabs((long long)b->prm.m), llabs((long long)b->prm.u), llabs((long long)b->prm.o), llabs((long long)b->prm.e), 1});
-	const bool p16_mode = b->mode == AT_LOCAL && b->prm.m >= b->prm.u && b->prm.m - b->prm.u <= 32 && !getenv("AT_NO_P16");
+	const bool p16_mode = b->mode == AT_LOCAL && llabs((long long)b->prm.m - b->prm.u) <= 31 && !getenv("AT_NO_P16");
 	auto p16_ok = [&](uint32_t l1, uint32_t l2) {
 		return p16_mode && l1 <= 32u * MAXR && l2 <= 60000u && 8 * (int64_t)(l1 + l2 + 2) * maxabs < 32000;
 	};
@@ -367,7 +367,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 			for (size_t x = 0; x < cand.size();) {
 				if (x + 1 < cand.size() && key(cand[x]) == key(cand[x + 1])) {
 					const int r = s.h_rclass[cand[x]] & 15;
-					c.h_jobs2[r].push_back(make_uint2(cand[x], cand[x + 1]));
+					c.h_jobs2[r].push_back(FillJob{cand[x], cand[x + 1]});
 					c.cells_r2[r] += cells_of(cand[x]) + cells_of(cand[x + 1]);
 					x += 2;
 				} else { scalar_pairs.push_back(cand[x]); x += 1; }
@@ -378,18 +378,18 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 			bool ragged = false;
 			for (size_t x = 1; x < scalar_pairs.size() && !ragged; ++x) ragged = cells_of(scalar_pairs[x]) != cells_of(scalar_pairs[0]);
 			if (ragged) std::stable_sort(scalar_pairs.begin(), scalar_pairs.end(), [&](uint32_t x, uint32_t y) { return cells_of(x) > cells_of(y); });
-			for (uint32_t k : scalar_pairs) { const int r = s.h_rclass[k] & 15; c.h_jobs[r].push_back(k); c.cells_r[r] += cells_of(k); }
+			for (uint32_t k : scalar_pairs) { const int r = s.h_rclass[k] & 15; c.h_jobs[r].push_back(FillJob{k, k}); c.cells_r[r] += cells_of(k); if (in->q_len[s.p0 + k] > 32u * MAXR) c.multi_r[r] = true; }
 		}
 		// ---- pointer blocks: one per int32 pair, one per packed job (shared by its two pairs) ----
 		c.h_ptr_off.assign(nc, 0);
 		uint64_t words = 0;
 		if (b->traceback) {
 			for (int r = 1; r <= MAXR; ++r) {
-				for (uint32_t k : c.h_jobs[r]) { c.h_ptr_off[k - c.k0] = words; words += ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]); }
-				for (const uint2 &jb : c.h_jobs2[r]) {
-					const uint32_t tl = (in->t_len[s.p0 + jb.x] + 31u) | 3u;
-					c.h_ptr_off[jb.x - c.k0] = words; c.h_ptr_off[jb.y - c.k0] = words;
-					s.h_rclass[jb.x] = (uint8_t)(r | (1 << 4)); s.h_rclass[jb.y] = (uint8_t)(r | (2 << 4));
+				for (const FillJob &jb : c.h_jobs[r]) { const uint32_t k = jb.a; c.h_ptr_off[k - c.k0] = words; words += ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]); }
+				for (const FillJob &jb : c.h_jobs2[r]) {
+					const uint32_t tl = (in->t_len[s.p0 + jb.a] + 31u) | 3u;
+					c.h_ptr_off[jb.a - c.k0] = words; c.h_ptr_off[jb.b - c.k0] = words;
+					s.h_rclass[jb.a] = (uint8_t)(r | (1 << 4)); s.h_rclass[jb.b] = (uint8_t)(r | (2 << 4));
 					words += (uint64_t)((tl >> 2) + 1) * r * 32;
 				}
 			}
@@ -400,11 +400,11 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		for (int r = 1; r <= MAXR; ++r) {
 			if (!c.h_jobs[r].empty()) {
 				CU(h, c.d_jobs[r].alloc(c.h_jobs[r].size()));
-				CU(h, cudaMemcpyAsync(c.d_jobs[r].p, c.h_jobs[r].data(), c.h_jobs[r].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+				CU(h, cudaMemcpyAsync(c.d_jobs[r].p, c.h_jobs[r].data(), c.h_jobs[r].size() * sizeof(FillJob), cudaMemcpyHostToDevice, st));
 			}
 			if (!c.h_jobs2[r].empty()) {
 				CU(h, c.d_jobs2[r].alloc(c.h_jobs2[r].size()));
-				CU(h, cudaMemcpyAsync(c.d_jobs2[r].p, c.h_jobs2[r].data(), c.h_jobs2[r].size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+				CU(h, cudaMemcpyAsync(c.d_jobs2[r].p, c.h_jobs2[r].data(), c.h_jobs2[r].size() * sizeof(FillJob), cudaMemcpyHostToDevice, st));
 			}
 		}
 		CU(h, c.d_ptr_off.alloc(nc));
@@ -475,93 +475,44 @@ extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const
 }
 
 // ------------------------------------------------------------------ launch ----
-template <int MODE, bool JUMP> struct AffineLauncher {
-	template <int R> static cudaError_t go(const FillArgs &fa, int blocks, cudaStream_t st) {
-		at_fill_affine<MODE, R, JUMP><<<blocks, 128, 0, st>>>(fa);
-		return cudaGetLastError();
-	}
-	template <int R> static int occ() {
-		int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_affine<MODE, R, JUMP>, 128, 0); return nb;
-	}
-};
-template <int MODE> struct LinearLauncher {
-	template <int R> static cudaError_t go(const FillArgs &fa, int blocks, cudaStream_t st) {
-		at_fill_linear<MODE, R><<<blocks, 128, 0, st>>>(fa);
-		return cudaGetLastError();
-	}
-	template <int R> static int occ() {
-		int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_linear<MODE, R>, 128, 0); return nb;
-	}
-};
+// Kernel table: mode variant x rows-per-lane x lanes.  kind: 0 global, 1 local, 2 fit, 3 fit+jump
+// (int32 lanes, optionally multi-stripe for R = 8), 4 local on packed s16x2 lanes, 5 overlap, 6 edit.
+typedef void (*fill2_fn)(const FillArgs2);
+typedef void (*fill1_fn)(const FillArgs);
 
-template <class L> static int occ_r(int R)
+template <int R> static fill2_fn affine_fn(int kind, bool multi)
+{
+	if (multi) {
+		switch (kind) {
+		case 0: return at_fill_affine<MODE_GLOBAL, 8, false, false, true>;
+		case 1: return at_fill_affine<MODE_LOCAL, 8, false, false, true>;
+		case 2: return at_fill_affine<MODE_FIT, 8, false, false, true>;
+		default: return at_fill_affine<MODE_FIT, 8, true, false, true>;
+		}
+	}
+	switch (kind) {
+	case 0: return at_fill_affine<MODE_GLOBAL, R, false, false, false>;
+	case 1: return at_fill_affine<MODE_LOCAL, R, false, false, false>;
+	case 2: return at_fill_affine<MODE_FIT, R, false, false, false>;
+	case 3: return at_fill_affine<MODE_FIT, R, true, false, false>;
+	default: return at_fill_affine<MODE_LOCAL, R, false, true, false>;
+	}
+}
+static fill2_fn affine_kernel(int kind, int R, bool multi)
 {
 	switch (R) {
-	case 1: return L::template occ<1>(); case 2: return L::template occ<2>(); case 3: return L::template occ<3>();
-	case 4: return L::template occ<4>(); case 5: return L::template occ<5>(); case 6: return L::template occ<6>();
-	case 7: return L::template occ<7>(); default: return L::template occ<8>();
+	case 1: return affine_fn<1>(kind, multi); case 2: return affine_fn<2>(kind, multi); case 3: return affine_fn<3>(kind, multi);
+	case 4: return affine_fn<4>(kind, multi); case 5: return affine_fn<5>(kind, multi); case 6: return affine_fn<6>(kind, multi);
+	case 7: return affine_fn<7>(kind, multi); default: return affine_fn<8>(kind, multi);
 	}
 }
-template <class L> static cudaError_t go_r(int R, const FillArgs &fa, int blocks, cudaStream_t st)
+template <int MODE> static fill1_fn linear_fn(int R)
 {
 	switch (R) {
-	case 1: return L::template go<1>(fa, blocks, st); case 2: return L::template go<2>(fa, blocks, st);
-	case 3: return L::template go<3>(fa, blocks, st); case 4: return L::template go<4>(fa, blocks, st);
-	case 5: return L::template go<5>(fa, blocks, st); case 6: return L::template go<6>(fa, blocks, st);
-	case 7: return L::template go<7>(fa, blocks, st); default: return L::template go<8>(fa, blocks, st);
+	case 1: return at_fill_linear<MODE, 1>; case 2: return at_fill_linear<MODE, 2>; case 3: return at_fill_linear<MODE, 3>;
+	case 4: return at_fill_linear<MODE, 4>; case 5: return at_fill_linear<MODE, 5>; case 6: return at_fill_linear<MODE, 6>;
+	case 7: return at_fill_linear<MODE, 7>; default: return at_fill_linear<MODE, 8>;
 	}
-}
-
-static int fill_occupancy(int mode, bool jump, int R)
-{
-	switch (mode) {
-	case AT_GLOBAL: return occ_r<AffineLauncher<MODE_GLOBAL, false>>(R);
-	case AT_LOCAL:  return occ_r<AffineLauncher<MODE_LOCAL, false>>(R);
-	case AT_FIT:    return jump ? occ_r<AffineLauncher<MODE_FIT, true>>(R) : occ_r<AffineLauncher<MODE_FIT, false>>(R);
-	case AT_OVERLAP: return occ_r<LinearLauncher<MODE_OVERLAP>>(R);
-	default:        return occ_r<LinearLauncher<MODE_EDIT>>(R);
-	}
-}
-static cudaError_t fill_launch(int mode, bool jump, int R, const FillArgs &fa, int blocks, cudaStream_t st)
-{
-	switch (mode) {
-	case AT_GLOBAL: return go_r<AffineLauncher<MODE_GLOBAL, false>>(R, fa, blocks, st);
-	case AT_LOCAL:  return go_r<AffineLauncher<MODE_LOCAL, false>>(R, fa, blocks, st);
-	case AT_FIT:    return jump ? go_r<AffineLauncher<MODE_FIT, true>>(R, fa, blocks, st) : go_r<AffineLauncher<MODE_FIT, false>>(R, fa, blocks, st);
-	case AT_OVERLAP: return go_r<LinearLauncher<MODE_OVERLAP>>(R, fa, blocks, st);
-	default:        return go_r<LinearLauncher<MODE_EDIT>>(R, fa, blocks, st);
-	}
-}
-
-static int p16_occupancy(int R)
-{
-	int nb = 0;
-	switch (R) {
-	case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<1>, 32 * AT_P16_WARPS, 0); break;
-	case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<2>, 32 * AT_P16_WARPS, 0); break;
-	case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<3>, 32 * AT_P16_WARPS, 0); break;
-	case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<4>, 32 * AT_P16_WARPS, 0); break;
-	case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<5>, 32 * AT_P16_WARPS, 0); break;
-	case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<6>, 32 * AT_P16_WARPS, 0); break;
-	case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<7>, 32 * AT_P16_WARPS, 0); break;
-	default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, at_fill_local_p16<8>, 32 * AT_P16_WARPS, 0); break;
-	}
-	return nb;
-}
-static cudaError_t p16_launch(int R, const FillArgsP16 &fa, int blocks, cudaStream_t st)
-{
-	const int th = 32 * AT_P16_WARPS;
-	switch (R) {
-	case 1: at_fill_local_p16<1><<<blocks, th, 0, st>>>(fa); break;
-	case 2: at_fill_local_p16<2><<<blocks, th, 0, st>>>(fa); break;
-	case 3: at_fill_local_p16<3><<<blocks, th, 0, st>>>(fa); break;
-	case 4: at_fill_local_p16<4><<<blocks, th, 0, st>>>(fa); break;
-	case 5: at_fill_local_p16<5><<<blocks, th, 0, st>>>(fa); break;
-	case 6: at_fill_local_p16<6><<<blocks, th, 0, st>>>(fa); break;
-	case 7: at_fill_local_p16<7><<<blocks, th, 0, st>>>(fa); break;
-	default: at_fill_local_p16<8><<<blocks, th, 0, st>>>(fa); break;
-	}
-	return cudaGetLastError();
 }
 
 struct CastU64 { __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; } };
@@ -591,52 +542,55 @@ static int run_shard(at_batch *b, Shard &s)
 		CU(h, cudaMemsetAsync(s.d_counter.p, 0, 64 * sizeof(uint32_t), st));
 		CU(h, cudaEventRecord(e_begin, st));
 		if (first) { CU(h, cudaEventRecord(e_first, st)); first = false; }
-		for (int r = 1; r <= MAXR; ++r) {
-			if (c.h_jobs[r].empty()) continue;
-			int occ = fill_occupancy(b->mode, jump, r);
-			if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, r); return AT_E_CUDA; }
-			const uint64_t warps_needed = c.h_jobs[r].size();
-			int blocks = s.dev->sm_count * occ;
-			blocks = (int)std::min<uint64_t>((uint64_t)blocks, (warps_needed + 3) / 4);
-			if (blocks < 1) blocks = 1;
-			if (s.multi_stripe) {     // one boundary slab per resident warp
-				const uint64_t stride = (uint64_t)s.max_l2 + 2;
-				if (s.d_bnd.alloc((size_t)blocks * 4 * stride) != cudaSuccess) { set_err(h, "stripe boundary slabs"); return AT_E_NOMEM; }
-			} else CU(h, s.d_bnd.alloc(1));
-			FillArgs fa;
-			fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
-			fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
-			fa.jmask = s.d_jmask.p; fa.jobs = c.d_jobs[r].p; fa.n_jobs = (uint32_t)c.h_jobs[r].size();
-			fa.counter = s.d_counter.p + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
-			fa.bnd = s.d_bnd.p; fa.bnd_stride = s.max_l2 + 2;
-			fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
-			fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
-			fa.want_ptr = b->traceback ? 1 : 0;
-			const bool dom = (int)ci == dom_chunk && r == dom_r;
-			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
-			CU(h, fill_launch(b->mode, jump, r, fa, blocks, st));
-			if (dom) CU(h, cudaEventRecord(s.evk[1], st));
-			s.launches++;
-		}
-		for (int r = 1; r <= MAXR; ++r) {          // packed s16x2 launches (local mode)
-			if (c.h_jobs2[r].empty()) continue;
-			int occ = p16_occupancy(r);
-			if (occ < 1) { set_err(h, "packed fill kernel (R %d) cannot be resident", r); return AT_E_CUDA; }
-			int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (c.h_jobs2[r].size() + AT_P16_WARPS - 1) / AT_P16_WARPS);
-			if (blocks < 1) blocks = 1;
-			FillArgsP16 fa;
-			fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
-			fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
-			fa.jobs = c.d_jobs2[r].p; fa.n_jobs = (uint32_t)c.h_jobs2[r].size();
-			fa.counter = s.d_counter.p + 16 + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
-			fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
-			fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e;
-			fa.want_ptr = b->traceback ? 1 : 0;
-			const bool dom = (int)ci == dom_chunk && r + 100 == dom_r;
-			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
-			CU(h, p16_launch(r, fa, blocks, st));
-			if (dom) CU(h, cudaEventRecord(s.evk[1], st));
-			s.launches++;
+		for (int pass = 0; pass < 2; ++pass) {      // pass 0: int32 lanes, pass 1: packed s16x2 lanes
+			for (int r = 1; r <= MAXR; ++r) {
+				std::vector<FillJob> &hj = pass ? c.h_jobs2[r] : c.h_jobs[r];
+				if (hj.empty()) continue;
+				const bool affine = b->mode <= AT_FIT;
+				const bool multi = !pass && c.multi_r[r];
+				const int kind = pass ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode);
+				const void *fn = affine ? (const void *)affine_kernel(kind, r, multi)
+				                        : (b->mode == AT_OVERLAP ? (const void *)linear_fn<MODE_OVERLAP>(r) : (const void *)linear_fn<MODE_EDIT>(r));
+				int occ = 0;
+				CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * AT_FILL_WARPS, 0));
+				if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, r); return AT_E_CUDA; }
+				int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (hj.size() + AT_FILL_WARPS - 1) / AT_FILL_WARPS);
+				if (blocks < 1) blocks = 1;
+				const bool need_bnd = multi || (!affine && c.multi_r[r]);
+				if (need_bnd) {     // one boundary slab per resident warp
+					const uint64_t stride = (uint64_t)s.max_l2 + 2;
+					if (s.d_bnd.alloc((size_t)blocks * AT_FILL_WARPS * stride) != cudaSuccess) { set_err(h, "stripe boundary slabs"); return AT_E_NOMEM; }
+				} else CU(h, s.d_bnd.alloc(1));
+				const bool dom = (int)ci == dom_chunk && (pass ? r + 100 : r) == dom_r;
+				if (dom) CU(h, cudaEventRecord(s.evk[0], st));
+				if (affine) {
+					FillArgs2 fa;
+					fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
+					fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
+					fa.jmask = s.d_jmask.p; fa.jobs = pass ? c.d_jobs2[r].p : c.d_jobs[r].p; fa.n_jobs = (uint32_t)hj.size();
+					fa.counter = s.d_counter.p + (pass ? 16 : 0) + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
+					fa.bnd = s.d_bnd.p; fa.bnd_stride = s.max_l2 + 2;
+					fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
+					fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
+					fa.want_ptr = b->traceback ? 1 : 0;
+					void *kargs[] = {(void *)&fa};
+					CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * AT_FILL_WARPS), kargs, 0, st));
+				} else {
+					FillArgs fa;
+					fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
+					fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
+					fa.jmask = nullptr; fa.jobs = (const uint32_t *)c.d_jobs[r].p; fa.n_jobs = (uint32_t)hj.size();
+					fa.counter = s.d_counter.p + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
+					fa.bnd = s.d_bnd.p; fa.bnd_stride = s.max_l2 + 2;
+					fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
+					fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
+					fa.want_ptr = b->traceback ? 1 : 0;
+					void *kargs[] = {(void *)&fa};
+					CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * AT_FILL_WARPS), kargs, 0, st));
+				}
+				if (dom) CU(h, cudaEventRecord(s.evk[1], st));
+				s.launches++;
+			}
 		}
 		CU(h, cudaEventRecord(e_fill, st));
 		if (b->traceback) {

@@ -30,10 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OPS_PER_CELL = {"global": 10, "local": 12, "fit": 10, "fitjump": 14, "overlap": 6, "edit": 6}
-# Integer issue rate MEASURED on this pool's B200 with tools/int_peak.cu (profiles/int_peak_r01.txt):
-# VIMNMX / VIADDMNMX / VIADD.16x2 / LOP3 / IMAD all sustain ~117.6 lane-ops/clk/SM (one warp
-# instruction per scheduler per clock), i.e. 128 nominal lanes, not the 64 SURVEY.md assumed.
-INT32_LANES_PER_SM_MEASURED = 117.6
+# Integer roofline denominator (BASELINE.md 4 / SURVEY.md 8d): the ALU pipe issues 64 int32 lanes per
+# clock per SM (ncu: sm__inst_executed_pipe_alu is the binding unit of the fill; tools/int_peak.cu
+# measures 56-59 lane-ops/clk/SM for VIMNMX / LOP3 / VIADDMNMX), and one packed s16x2 instruction
+# counts as two operations.  profiles/int_peak_r01.txt has the raw numbers.
+INT32_LANES_PER_SM = 64
 NCU_TRAFFIC_BYTES_PER_LAUNCH = None   # dram read+write of one dominant-kernel launch, from profiles/ (ncu --set full)
 PACKED_FACTOR = 2          # one s16x2 instruction advances two cells ("x2 counted for packed s16x2")
 
@@ -270,14 +271,14 @@ def main():
     # ---------------- roofline of the dominant kernel (the local fill) ----------------
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
     k_ms = sum(kern_ms) / len(kern_ms)
-    int_peak = 148 * INT32_LANES_PER_SM_MEASURED * PACKED_FACTOR * sm_max_mhz * 1e6 / 1e12     # T int-op/s
+    int_peak = 148 * INT32_LANES_PER_SM * PACKED_FACTOR * sm_max_mhz * 1e6 / 1e12     # T int-op/s
     achieved = tm.fill_kernel_cells * OPS_PER_CELL["local"] / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "int_alu", "achieved": achieved, "peak": int_peak, "unit": "Tiop/s", "frac": achieved / int_peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "at_fill_local_p16<R=5>", "kernel_ms": k_ms,
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "at_fill_affine<LOCAL,R=5,s16x2>", "kernel_ms": k_ms,
                 "kernel_gcups": tm.fill_kernel_cells / (k_ms * 1e-3) / 1e9,
                 "ops_per_cell": OPS_PER_CELL["local"],
-                "peak_note": (f"148 SM x {INT32_LANES_PER_SM_MEASURED} lane-ops/clk/SM (measured, tools/int_peak.cu) x {PACKED_FACTOR} "
-                              f"(s16x2) x {sm_max_mhz:.0f} MHz; algorithmic ops/cell from SURVEY.md 8(d)"),
+                "peak_note": (f"148 SM x {INT32_LANES_PER_SM} ALU lanes x {PACKED_FACTOR} (s16x2) x {sm_max_mhz:.0f} MHz nominal "
+                              "(BASELINE.md 4); algorithmic ops/cell from SURVEY.md 8(d)"),
                 "hbm": {"bound": "hbm", "achieved": tm.ptr_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": tm.ptr_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "what": "traceback-pointer writes", "peak_src": peak_src}}
 

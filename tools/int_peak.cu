@@ -51,7 +51,7 @@ __global__ void k(int *out, int a0, int b0, long long *clk)
 
 template <int OP> static void run(int sms, int *d_out, long long *d_clk)
 {
-	const int blocks = sms * 2, threads = 1024;
+	const int blocks = sms, threads = 1024;      // one 1024-thread block per SM (two do not co-reside: they ran back to back)
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	k<OP><<<blocks, threads>>>(d_out, 1, 3, d_clk);
 	cudaEventRecord(e0);
@@ -60,8 +60,8 @@ template <int OP> static void run(int sms, int *d_out, long long *d_clk)
 	float ms; cudaEventElapsedTime(&ms, e0, e1);
 	long long clk0; cudaMemcpy(&clk0, d_clk, sizeof clk0, cudaMemcpyDeviceToHost);
 	const double ops = (double)blocks * threads * ITERS * ILP;
-	// per-SM: 2 blocks of 1024 threads resident => 2048 threads; cycles from clock64 of block 0
-	const double per_clk_sm = 2048.0 * ITERS * ILP / (double)clk0;
+	// per-SM rate from the in-kernel cycle counter of block 0 (1024 threads resident per SM)
+	const double per_clk_sm = 1024.0 * ITERS * ILP / (double)clk0;
 	printf("%-26s %8.3f ms  %7.2f Tlane-op/s  %6.1f lane-ops/clk/SM  (block0 %lld clk)\n", NAMES[OP], ms, ops / ms / 1e9, per_clk_sm, clk0);
 }
 
@@ -70,7 +70,7 @@ int main()
 	cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
 	printf("device: %s, %d SMs, clockRate %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
 	int *d_out; long long *d_clk;
-	cudaMalloc(&d_out, sizeof(int) * p.multiProcessorCount * 2 * 1024);
+	cudaMalloc(&d_out, sizeof(int) * p.multiProcessorCount * 1024);
 	cudaMalloc(&d_clk, sizeof(long long) * p.multiProcessorCount * 2);
 	run<OP_IADD>(p.multiProcessorCount, d_out, d_clk);
 	run<OP_MAX>(p.multiProcessorCount, d_out, d_clk);
