@@ -278,18 +278,18 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true);
 				}
 				if (want_ptr) {
-					uint32_t *w = ptr + ((size_t)(stripe * G + tb / SPW) * R) * 32 + lane;
+					uint32_t *w = ptr + ((size_t)(stripe * G + tb / SPW) * 32 + lane) * R;
 #pragma unroll
-					for (int r = 0; r < R; ++r) w[r * 32] = acc[r];
+					for (int r = 0; r < R; ++r) w[r] = acc[r];
 				}
 				if (PACKED) {
 #pragma unroll
 					for (int r = 0; r < R; ++r) acc[r] = 0;   // 4 nibbles per half: the next shift must not spill A's bits into B's half
 				}
 				if (JUMP && want_ptr && ((tb + SPW - 1u) & 31u) == 31u) {
-					uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (tb >> 5)) * R) * 32 + lane;
+					uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (tb >> 5)) * 32 + lane) * R;
 #pragma unroll
-					for (int r = 0; r < R; ++r) w[r * 32] = accJ[r];
+					for (int r = 0; r < R; ++r) w[r] = accJ[r];
 				}
 			}
 

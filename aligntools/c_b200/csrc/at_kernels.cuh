@@ -2,8 +2,10 @@
 //
 // K1  at_fill_affine<MODE,R,JUMP>  : Gotoh M/L/U(/J) fill, one pair per warp, int32 lanes.
 //     at_fill_linear<MODE,R>       : single-plane fill (overlap max-plus / edit min-plus).
-// K3  at_traceback<...>            : device traceback, one thread per pair, two walks
-//                                    (count, then emit CIGAR runs + gapped strings).
+// K3  at_traceback_walk            : device traceback, one thread per pair chases the pointers
+//                                    once and leaves the reversed run-length ops in scratch;
+//     at_traceback_emit            : one warp per pair writes the dense CIGAR and replays it over
+//                                    the sequences into the gapped strings r1 / r2.
 //
 // Geometry.  Rows i <-> read s1, columns j <-> target s2.  A warp
 // sweeps a STRIPE of 32*R rows over all columns as a systolic array: lane k owns rows
@@ -18,8 +20,10 @@
 // extended); fit+jump adds a 1-bit plane (pointerJ is JUMP).  Reference planes:
 // src/alignment.h:44-47, values :27-34.  Nibbles of 8 consecutive steps of one row are
 // packed into a 32-bit word (earliest step in the top nibble) and stored as
-//   word[((stripe*G + step/8)*R + r)*32 + lane]           (128-byte coalesced rows)
-// i.e. in SKEWED coordinates (step = column + lane), so every store is a full line.
+//   word[((stripe*G + step/8)*32 + lane)*R + r]
+// i.e. in SKEWED coordinates (step = column + lane) with the R words of a lane's 8-step block
+// contiguous: a warp flush writes one dense 128*R-byte run, and a diagonal traceback move
+// (row-1, column-1) stays inside the same 32-byte sector most of the time.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -134,9 +138,9 @@ __device__ __forceinline__ void fill_linear_pair(const FillArgs &a, const uint32
 				for (int r = 0; r < R; ++r) acc[r] <<= 2;
 			}
 			if (want_ptr && (t & 15u) == 15u) {
-				uint32_t *w = ptr + ((size_t)(stripe * G + (t >> 4)) * R) * 32 + lane;
+				uint32_t *w = ptr + ((size_t)(stripe * G + (t >> 4)) * 32 + lane) * R;
 #pragma unroll
-				for (int r = 0; r < R; ++r) w[r * 32] = acc[r];
+				for (int r = 0; r < R; ++r) w[r] = acc[r];
 			}
 		}
 		__syncwarp();
@@ -173,15 +177,17 @@ struct TraceArgs {
 	const uint8_t  *t;  const uint64_t *t_off;  const uint32_t *t_len;
 	const uint32_t *ptr; const uint64_t *ptr_off;
 	const uint8_t  *rclass;    // [pair] bits 0-3: rows-per-lane R the fill used; bits 4-5: 0 = int32 layout,
-	                           //        1 / 2 = packed s16x2 layout, pair in the low / high half (at_kernels_p16.cuh)
+	                           //        1 / 2 = packed s16x2 layout, pair in the low / high half
 	uint32_t        pair_base, n_pairs;   // chunk
 	const uint32_t *end_i, *end_j; const uint8_t *end_state;
 	uint32_t       *beg_i, *beg_j;
-	uint32_t       *n_ops, *n_cols;       // [pair] written by the count walk
+	uint32_t       *n_ops, *n_cols;       // [pair]
+	uint32_t       *scratch;              // reversed run-length ops, slot of l1+l2 ops per pair
+	const uint64_t *scratch_off;          // [n_chunk] chunk-local slot offsets
 	const uint64_t *ops_off, *cols_off;   // [n_chunk+1] exclusive scans (chunk-local index)
 	uint32_t       *cigar;                // dense ops of the chunk
 	uint8_t        *aln1, *aln2;          // dense columns of the chunk
-	int             mode, jump, emit;
+	int             mode, jump;
 };
 
 struct PtrView {
@@ -190,67 +196,57 @@ struct PtrView {
 	__device__ __forceinline__ uint32_t nib(uint32_t i, uint32_t j) const {
 		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
 		if (half) {   // packed s16x2: 4 steps x 2 pairs per word, single stripe
-			const uint32_t w = __ldg(ptr + ((size_t)(t >> 2) * R + r) * 32 + lane);
+			const uint32_t w = __ldg(ptr + ((size_t)(t >> 2) * 32 + lane) * R + r);
 			return (w >> (16 * (half - 1) + 4 * (3 - (t & 3)))) & 15u;
 		}
-		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 3)) * R + r) * 32 + lane);
+		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 3)) * 32 + lane) * R + r);
 		return (w >> (4 * (7 - (t & 7)))) & 15u;
 	}
 	__device__ __forceinline__ uint32_t jbit(uint32_t i, uint32_t j) const {
 		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
-		const uint32_t w = __ldg(ptrJ + ((size_t)(stripe * GJ + (t >> 5)) * R + r) * 32 + lane);
+		const uint32_t w = __ldg(ptrJ + ((size_t)(stripe * GJ + (t >> 5)) * 32 + lane) * R + r);
 		return (w >> (31 - (t & 31))) & 1u;
 	}
 	__device__ __forceinline__ uint32_t two(uint32_t i, uint32_t j) const {   // overlap: 2 bits, 16 steps per word
 		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
-		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 4)) * R + r) * 32 + lane);
+		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 4)) * 32 + lane) * R + r);
 		return (w >> (2 * (15 - (t & 15)))) & 3u;
 	}
 };
 
-struct Emitter {
-	uint32_t *cig; uint8_t *a1, *a2; bool emit;
-	uint32_t n_ops, n_cols, run, op; uint32_t tot_ops, tot_cols;
-	__device__ __forceinline__ void flush_run() {
-		if (run) { if (cig) cig[tot_ops - 1 - n_ops] = (run << 4) | op; ++n_ops; }
-	}
-	__device__ __forceinline__ void col(uint32_t o, uint8_t x, uint8_t y) {
-		if (run && o != op) { flush_run(); run = 0; }
-		op = o; ++run;
-		if (a1) { a1[tot_cols - 1 - n_cols] = x; a2[tot_cols - 1 - n_cols] = y; }
-		++n_cols;
-	}
+// run-length encoder writing ops in walk (= reverse) order
+struct RunWriter {
+	uint32_t *dst; uint32_t n_ops, n_cols, run, op;
+	__device__ __forceinline__ void flush() { if (run) dst[n_ops++] = (run << 4) | op; run = 0; }
+	__device__ __forceinline__ void col(uint32_t o) { if (run && o != op) flush(); op = o; ++run; ++n_cols; }
 };
 
-__global__ void __launch_bounds__(128) at_traceback(const TraceArgs a)
+// One thread per pair: chase the pointers once, leave the reversed CIGAR in the pair's scratch slot.
+__global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= a.n_pairs) return;
 	const uint32_t p = a.pair_base + k;
 	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
-	const uint8_t *q = a.q + a.q_off[p], *tg = a.t + a.t_off[p];
 	PtrView pv;
 	pv.R = a.rclass[p] & 15u; pv.RPP = 32 * pv.R; pv.half = (a.rclass[p] >> 4) & 3u;
 	const uint32_t n_stripes = (l1 + pv.RPP - 1) / pv.RPP;
 	const bool jump = a.jump != 0;
 	if (a.mode == MODE_OVERLAP) { const uint32_t tl = steps_last(l2, 15); pv.G = (tl >> 4) + 1; pv.GJ = 0; }
+	else if (pv.half) { const uint32_t tl = steps_last(l2, 3); pv.G = (tl >> 2) + 1; pv.GJ = 0; }
 	else { const uint32_t tl = steps_last(l2, jump ? 31 : 7); pv.G = (tl >> 3) + 1; pv.GJ = (tl >> 5) + 1; }
 	pv.ptr = a.ptr + a.ptr_off[k];
 	pv.ptrJ = pv.ptr + (size_t)n_stripes * pv.G * pv.RPP;
-	Emitter em;
-	em.emit = a.emit != 0; em.n_ops = em.n_cols = em.run = 0; em.op = 0;
-	em.tot_ops = em.emit ? a.n_ops[p] : 0; em.tot_cols = em.emit ? a.n_cols[p] : 0;
-	em.cig = em.emit && a.cigar ? a.cigar + a.ops_off[k] : nullptr;
-	em.a1 = em.emit && a.aln1 ? a.aln1 + a.cols_off[k] : nullptr;
-	em.a2 = em.emit && a.aln2 ? a.aln2 + a.cols_off[k] : nullptr;
+	RunWriter w;
+	w.dst = a.scratch + a.scratch_off[k]; w.n_ops = w.n_cols = w.run = 0; w.op = 0;
 	uint32_t i = a.end_i[p], j = a.end_j[p], state = a.end_state[p];
 
 	if (a.mode == MODE_OVERLAP) {
 		while (j > 0) {                                   // :899
 			const uint32_t c = pv.two(i, j);
-			if (c == 1)      { --j; em.col(CIG_D, '-', tg[j]); }               // LEFT
-			else if (c == 2) { --i; --j; em.col(CIG_M, q[i], tg[j]); }         // DIAGONAL
-			else if (c == 3) { --i; em.col(CIG_I, q[i], '-'); }                // RIGHT
+			if (c == 1)      { --j; w.col(CIG_D); }                  // LEFT
+			else if (c == 2) { --i; --j; w.col(CIG_M); }             // DIAGONAL
+			else if (c == 3) { --i; w.col(CIG_I); }                  // RIGHT
 			else break;                                   // unset pointer: unreachable on a finite path
 		}
 	} else {
@@ -260,24 +256,54 @@ __global__ void __launch_bounds__(128) at_traceback(const TraceArgs a)
 			if (!go || home) break;
 			if (j == 0 && state != ST_LOW) break;         // only reachable with corrupt pointers: never index s2[-1]
 			const uint32_t nb = pv.nib(i, j);
-			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; em.col(CIG_I, q[i], '-'); }
+			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; w.col(CIG_I); }
 			else if (state == ST_MID) {
 				const uint32_t pm = nb & 3u;
-				--i; --j; em.col(CIG_M, q[i], tg[j]);
+				--i; --j; w.col(CIG_M);
 				if (pm == 3 && a.mode == MODE_LOCAL) home = true;              // HOME: column emitted, then stop (:788-791)
 				else state = pm;
 			}
-			else if (state == ST_UPP) { state = (nb & 8u) ? ST_UPP : ST_MID; --j; em.col(CIG_D, '-', tg[j]); }
-			else                      { state = pv.jbit(i, j) ? ST_JUMP : ST_MID; --j; em.col(CIG_N, '-', tg[j]); }
+			else if (state == ST_UPP) { state = (nb & 8u) ? ST_UPP : ST_MID; --j; w.col(CIG_D); }
+			else                      { state = pv.jbit(i, j) ? ST_JUMP : ST_MID; --j; w.col(CIG_N); }
 		}
 	}
-	const uint32_t bi = i, bjj = j;
-	if (a.mode == MODE_GLOBAL) {                          // flush (:398-407)
-		while (j > 0) { --j; em.col(CIG_D, '-', tg[j]); }
-		while (i > 0) { --i; em.col(CIG_I, q[i], '-'); }
+	a.beg_i[p] = i; a.beg_j[p] = j;
+	if (a.mode == MODE_GLOBAL) {                          // flush (:398-407): rest of the target, then rest of the read
+		while (j > 0) { --j; w.col(CIG_D); }
+		while (i > 0) { --i; w.col(CIG_I); }
 	}
-	em.flush_run();
-	if (!em.emit) { a.n_ops[p] = em.n_ops; a.n_cols[p] = em.n_cols; a.beg_i[p] = bi; a.beg_j[p] = bjj; }
+	w.flush();
+	a.n_ops[p] = w.n_ops; a.n_cols[p] = w.n_cols;
+}
+
+// One warp per pair: reverse the scratch ops into the dense CIGAR and, on request, replay them
+// forward over the two sequences to write the gapped strings r1 / r2 (coalesced).
+__global__ void __launch_bounds__(128) at_traceback_emit(const TraceArgs a)
+{
+	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (k >= a.n_pairs) return;
+	const uint32_t p = a.pair_base + k;
+	const uint32_t n = a.n_ops[p];
+	const uint32_t *src = a.scratch + a.scratch_off[k];
+	if (a.cigar) {
+		uint32_t *dst = a.cigar + a.ops_off[k];
+		for (uint32_t x = lane; x < n; x += 32) dst[x] = src[n - 1 - x];
+	}
+	if (a.aln1) {
+		const uint8_t *q = a.q + a.q_off[p], *tg = a.t + a.t_off[p];
+		uint8_t *a1 = a.aln1 + a.cols_off[k], *a2 = a.aln2 + a.cols_off[k];
+		uint32_t i = a.mode == MODE_GLOBAL ? 0 : a.beg_i[p], j = a.mode == MODE_GLOBAL ? 0 : a.beg_j[p], col = 0;
+		for (uint32_t x = 0; x < n; ++x) {
+			const uint32_t op = src[n - 1 - x], len = op >> 4, code = op & 15u;
+			const bool gap1 = code == CIG_D || code == CIG_N, gap2 = code == CIG_I;
+			for (uint32_t c = lane; c < len; c += 32) {
+				a1[col + c] = gap1 ? (uint8_t)'-' : q[i + c];
+				a2[col + c] = gap2 ? (uint8_t)'-' : tg[j + c];
+			}
+			col += len; if (!gap1) i += len; if (!gap2) j += len;
+		}
+	}
 }
 
 // fit+jump: expand the per-pair blacklists into a byte mask aligned with the target bytes.

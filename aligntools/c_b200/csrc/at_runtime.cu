@@ -89,6 +89,11 @@ extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
 		if (cudaGetDeviceProperties(&prop, id) != cudaSuccess || prop.major < 10) { delete h; return AT_E_CUDA; }
 		at_device d; d.id = id; d.sm_count = prop.multiProcessorCount;
 		if (cudaSetDevice(id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return AT_E_CUDA; }
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+			uint64_t keep = UINT64_MAX;      // keep freed blocks cached in the pool (trimmed in at_destroy)
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
 		h->devs.push_back(d);
 	}
 	*out = h;
@@ -98,7 +103,12 @@ extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
 extern "C" void at_destroy(at_handle *h)
 {
 	if (!h) return;
-	for (auto &d : h->devs) { cudaSetDevice(d.id); if (d.stream) cudaStreamDestroy(d.stream); }
+	for (auto &d : h->devs) {
+		cudaSetDevice(d.id);
+		if (d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, d.id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+	}
 	delete h;
 }
 
@@ -107,16 +117,21 @@ extern "C" int at_device_count(const at_handle *h) { return h ? (int)h->devs.siz
 extern "C" uint64_t at_launch_count(const at_handle *h) { return h ? h->launches.load() : 0; }
 
 // ------------------------------------------------------------------- batch ----
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync); at_create
+// raises the pool's release threshold so that the 40+ GB pointer arena of one batch is handed to
+// the next batch without going back to the driver.  tl_stream is the calling shard's stream.
+static thread_local cudaStream_t tl_stream = nullptr;
+
 template <class T> struct DevBuf {
 	T *p = nullptr; size_t n = 0;
 	cudaError_t alloc(size_t count) {
 		if (count <= n && p) return cudaSuccess;
 		release();
-		cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
-		if (e == cudaSuccess) n = count; else p = nullptr;
+		cudaError_t e = cudaMallocAsync((void **)&p, std::max<size_t>(count, 1) * sizeof(T), tl_stream);
+		if (e == cudaSuccess) n = count; else { p = nullptr; cudaGetLastError(); }
 		return e;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	void release() { if (p) cudaFreeAsync(p, tl_stream); p = nullptr; n = 0; }
 };
 
 static const int MAXR = 8;
@@ -133,7 +148,8 @@ struct Chunk {
 	std::vector<FillJob> h_jobs2[MAXR + 1]; // packed s16x2 lanes: two pairs per warp
 	DevBuf<FillJob> d_jobs2[MAXR + 1];
 	uint64_t cells_r2[MAXR + 1] = {0};
-	DevBuf<uint64_t> d_ops_off, d_cols_off;
+	DevBuf<uint64_t> d_ops_off, d_cols_off, d_scratch_off;
+	std::vector<uint64_t> h_scratch_off; uint64_t scratch_words = 0;
 	DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_aln1, d_aln2;
 	uint64_t tot_ops = 0, tot_cols = 0;
 };
@@ -146,7 +162,7 @@ struct Shard {
 	DevBuf<uint64_t> d_q_off, d_t_off, d_site_off;
 	DevBuf<uint32_t> d_q_len, d_t_len, d_end_i, d_end_j, d_beg_i, d_beg_j, d_n_ops, d_n_cols, d_counter;
 	DevBuf<int32_t> d_score, d_sites;
-	DevBuf<uint32_t> d_ptr; DevBuf<int4> d_bnd; DevBuf<uint8_t> d_scan_tmp;
+	DevBuf<uint32_t> d_ptr, d_scratch; DevBuf<int4> d_bnd; DevBuf<uint8_t> d_scan_tmp;
 	std::vector<uint8_t> h_rclass;
 	std::vector<Chunk> chunks;
 	uint32_t max_l2 = 0; bool multi_stripe = false;
@@ -250,16 +266,16 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 
 static void free_shard(Shard &s)
 {
-	if (s.dev) cudaSetDevice(s.dev->id);
+	if (s.dev) { cudaSetDevice(s.dev->id); tl_stream = s.dev->stream; }
 	s.d_q.release(); s.d_t.release(); s.d_jmask.release(); s.d_rclass.release(); s.d_end_state.release();
 	s.d_q2.release(); s.d_t2.release();
 	s.d_q_off.release(); s.d_t_off.release(); s.d_site_off.release();
 	s.d_q_len.release(); s.d_t_len.release(); s.d_end_i.release(); s.d_end_j.release(); s.d_beg_i.release();
 	s.d_beg_j.release(); s.d_n_ops.release(); s.d_n_cols.release(); s.d_counter.release();
-	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_bnd.release(); s.d_scan_tmp.release();
+	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_scratch.release(); s.d_bnd.release(); s.d_scan_tmp.release();
 	for (auto &c : s.chunks) {
 		c.d_ptr_off.release(); for (auto &j : c.d_jobs) j.release(); for (auto &j : c.d_jobs2) j.release();
-		c.d_ops_off.release(); c.d_cols_off.release(); c.d_cigar.release(); c.d_aln1.release(); c.d_aln2.release();
+		c.d_ops_off.release(); c.d_cols_off.release(); c.d_scratch_off.release(); c.d_cigar.release(); c.d_aln1.release(); c.d_aln2.release();
 	}
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
 	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
@@ -277,6 +293,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	at_handle *h = b->h;
 	CU(h, cudaSetDevice(s.dev->id));
 	cudaStream_t st = s.dev->stream;
+	tl_stream = st;
 	const uint32_t n = s.n;
 	int rc;
 	if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len))) return rc;
@@ -323,6 +340,13 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	// ---- chunking by pointer-arena budget ----
 	size_t free_b = 0, total_b = 0;
 	CU(h, cudaMemGetInfo(&free_b, &total_b));
+	{   // blocks cached in the stream-ordered pool are reusable by this batch: count them as free
+		cudaMemPool_t pool; uint64_t reserved = 0, used = 0;
+		if (cudaDeviceGetDefaultMemPool(&pool, s.dev->id) == cudaSuccess &&
+		    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+		    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+			free_b += (size_t)(reserved - used);
+	}
 	uint64_t budget_words = (uint64_t)(free_b * 0.45) / 4;
 	if (const char *env = getenv("AT_PTR_BUDGET_MB")) budget_words = (uint64_t)atoll(env) * (1ull << 20) / 4;
 	// packed s16x2 lanes (two pairs per warp): local mode, scores x8 must fit int16, 8|m-u| < 256 (symbols are << 8)
@@ -332,7 +356,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		return p16_mode && l1 <= 32u * MAXR && l2 <= 60000u && 8 * (int64_t)(l1 + l2 + 2) * maxabs < 32000;
 	};
 	s.chunks.clear();
-	uint64_t max_chunk_words = 0;
+	uint64_t max_chunk_words = 0, max_scratch_words = 0;
 	{
 		Chunk cur; cur.k0 = 0;
 		uint64_t words = 0;
@@ -409,9 +433,20 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		}
 		CU(h, c.d_ptr_off.alloc(nc));
 		CU(h, cudaMemcpyAsync(c.d_ptr_off.p, c.h_ptr_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-		if (b->traceback) { CU(h, c.d_ops_off.alloc(nc + 1)); CU(h, c.d_cols_off.alloc(nc + 1)); }
+		if (b->traceback) {
+			CU(h, c.d_ops_off.alloc(nc + 1)); CU(h, c.d_cols_off.alloc(nc + 1));
+			// traceback scratch: a slot of l1+l2 run-length ops per pair (an alignment has at most l1+l2 columns)
+			c.h_scratch_off.resize(nc);
+			uint64_t sw = 0;
+			for (uint32_t k = 0; k < nc; ++k) { c.h_scratch_off[k] = sw; sw += (uint64_t)in->q_len[s.p0 + c.k0 + k] + in->t_len[s.p0 + c.k0 + k]; }
+			c.scratch_words = sw;
+			max_scratch_words = std::max(max_scratch_words, sw);
+			CU(h, c.d_scratch_off.alloc(nc));
+			CU(h, cudaMemcpyAsync(c.d_scratch_off.p, c.h_scratch_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		}
 		CU(h, cudaStreamSynchronize(st));
 	}
+	if (max_scratch_words && s.d_scratch.alloc(max_scratch_words) != cudaSuccess) { set_err(h, "traceback scratch of %llu MB", (unsigned long long)(max_scratch_words >> 18)); return AT_E_NOMEM; }
 	CU(h, s.d_rclass.alloc(n));
 	CU(h, cudaMemcpyAsync(s.d_rclass.p, s.h_rclass.data(), n, cudaMemcpyHostToDevice, st));
 	CU(h, cudaStreamSynchronize(st));
@@ -522,6 +557,7 @@ static int run_shard(at_batch *b, Shard &s)
 	at_handle *h = b->h;
 	CU(h, cudaSetDevice(s.dev->id));
 	cudaStream_t st = s.dev->stream;
+	tl_stream = st;
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
 	s.fill_ms = s.tb_ms = s.dev_ms = s.domk_ms = 0; s.domk_cells = 0; s.launches = 0;
 	// dominant (most cells) fill launch of the whole shard -> per-launch timing for the roofline
@@ -602,17 +638,16 @@ static int run_shard(at_batch *b, Shard &s)
 			ta.end_i = s.d_end_i.p; ta.end_j = s.d_end_j.p; ta.end_state = s.d_end_state.p;
 			ta.beg_i = s.d_beg_i.p; ta.beg_j = s.d_beg_j.p; ta.n_ops = s.d_n_ops.p; ta.n_cols = s.d_n_cols.p;
 			ta.ops_off = c.d_ops_off.p; ta.cols_off = c.d_cols_off.p;
+			ta.scratch = s.d_scratch.p; ta.scratch_off = c.d_scratch_off.p;
 			ta.cigar = nullptr; ta.aln1 = nullptr; ta.aln2 = nullptr;
-			ta.mode = b->mode; ta.jump = jump ? 1 : 0; ta.emit = 0;
-			const int tb_blocks = (int)((nc + 127) / 128);
-			at_traceback<<<tb_blocks, 128, 0, st>>>(ta);
+			ta.mode = b->mode; ta.jump = jump ? 1 : 0;
+			at_traceback_walk<<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
-			// exclusive scans (CUB): n_ops[k0..k1) + trailing slot -> offsets[nc+1]
+			// inclusive scans (CUB) of n_ops / n_cols into offsets[1..nc]; offsets[0] = 0
 			size_t tmp_bytes = 0;
 			cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_ops(s.d_n_ops.p + c.k0, CastU64());
 			cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_cols(s.d_n_cols.p + c.k0, CastU64());
-			// the slot after the chunk must read as zero for the total: scan nc items and add the tail on the host
 			CU(h, cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
 			CU(h, s.d_scan_tmp.alloc(tmp_bytes + 16));
 			CU(h, cudaMemsetAsync(c.d_ops_off.p, 0, sizeof(uint64_t), st));
@@ -629,8 +664,7 @@ static int run_shard(at_batch *b, Shard &s)
 			if (want_aln) { if (c.d_aln1.alloc(c.tot_cols + 1) != cudaSuccess || c.d_aln2.alloc(c.tot_cols + 1) != cudaSuccess) { set_err(h, "alignment buffer"); return AT_E_NOMEM; } }
 			ta.cigar = want_cig ? c.d_cigar.p : nullptr;
 			ta.aln1 = want_aln ? c.d_aln1.p : nullptr; ta.aln2 = want_aln ? c.d_aln2.p : nullptr;
-			ta.emit = 1;
-			at_traceback<<<tb_blocks, 128, 0, st>>>(ta);
+			at_traceback_emit<<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
 		}

@@ -250,13 +250,18 @@ def main():
             barrier()
             t1 = time.perf_counter()
             b2 = al.batch("local", opt, q, qo, ql, t, to, tl, out_flags=A.OUT_CIGAR)   # H2D from pinned memory
+            t2 = time.perf_counter()
             b2.run()
+            t3 = time.perf_counter()
             r2 = b2.fetch()                                                            # D2H of score / end cells / CIGAR
+            t4 = time.perf_counter()
             b2.free()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t1
             if k:
                 e2e_times.append(dt)
+                e2e_parts = {"create_h2d_ms": 1e3 * (t2 - t1), "run_ms": 1e3 * (t3 - t2), "fetch_d2h_ms": 1e3 * (t4 - t3),
+                             "free_ms": 1e3 * (dt - (t4 - t1))}
             d2h = r2.score.nbytes + 4 * r2.end_i.nbytes + r2.cigar_off.nbytes + int(r2.cigar_off[-1]) * 4
         e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
         if use_dist:
@@ -265,7 +270,7 @@ def main():
             e2e_ms = float(tt[0])
         assert int(r2.score.astype(np.int64).sum()) == score_sum
         e2e = {"value": cells * world / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "breakdown": e2e_parts,
                "api": "at_batch_create + at_batch_run + at_batch_fetch (pinned host buffers in, host buffers out)"}
 
     # ---------------- roofline of the dominant kernel (the local fill) ----------------
