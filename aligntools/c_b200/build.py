@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaligntools_b200.so")
 SOURCES = ["at_runtime.cu", "at_shim.cu"]
-HEADERS = ["at_kernels.cuh", "at_fill_affine.cuh", os.path.join("..", "..", "..", "include", "aligntools_b200.h")]
+HEADERS = ["at_kernels.cuh", "at_fill_affine.cuh", "at_wavefront.cuh", os.path.join("..", "..", "..", "include", "aligntools_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--threads", "0"]
 

@@ -1,10 +1,9 @@
 // at_fill_affine.cuh -- K1: Gotoh M/L/U(/J) fill for global / local / fit (+jump), sm_100a.
-// (included by at_kernels.cuh after FillArgs / constants)
+// (included by at_kernels.cuh after the constants)
 //
-// One kernel template, two kinds of score lanes:
-//   Lanes<false>  int32   : one pair per warp, any length (reads longer than 32*R rows are cut
-//                           into stripes; lane 31 parks its last row in a boundary slab that
-//                           lane 0 reads back on the next stripe), every mode.
+// Inter-pair kernel for SHORT reads (l1 <= 256 rows = 32 lanes x R <= 8 rows); longer reads go
+// to the stripe-pipelined K2 (at_wavefront.cuh).  One kernel template, two kinds of score lanes:
+//   Lanes<false>  int32   : one pair per warp, every mode.
 //   Lanes<true>   s16x2   : TWO pairs per warp, pair A in bits 0-15 and pair B in bits 16-31 of
 //                           every register (VIMNMX.U16x2 / VIADDMNMX.U16x2 DPX instructions);
 //                           local mode, single stripe, both pairs share l2.
@@ -76,24 +75,22 @@ struct FillArgs2 {
 	uint32_t        n_jobs;
 	uint32_t       *counter;
 	uint32_t       *ptr;     const uint64_t *ptr_off;   uint32_t pair_base;
-	int4           *bnd;     uint32_t bnd_stride;
 	int32_t        *score;   uint32_t *end_i;  uint32_t *end_j;  uint8_t *end_state;
 	int             m, u, o, e, jp;
 	int             want_ptr;
 };
 
-template <int MODE, int R, bool JUMP, bool PACKED, bool MULTI>
+template <int MODE, int R, bool JUMP, bool PACKED>
 __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillArgs2 a)
 {
 	typedef Lanes<PACKED> V;
 	typedef typename V::T T;
-	static_assert(!PACKED || (MODE == MODE_LOCAL && !JUMP && !MULTI), "packed lanes: local, single stripe");
+	static_assert(!PACKED || (MODE == MODE_LOCAL && !JUMP), "packed lanes: local mode");
 	constexpr uint32_t SPW = V::STEPS_PER_WORD;
 	constexpr int RPP = 32 * R;
 
 	__shared__ uint32_t ring_all[AT_FILL_WARPS][AT_RING];
 	const int lane = threadIdx.x & 31;
-	const uint32_t warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	uint32_t *ring = ring_all[threadIdx.x >> 5];
 
 	const int m = a.m, u = a.u, o = a.o, e = a.e;
@@ -118,9 +115,8 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 		uint32_t *__restrict__ ptr = a.ptr + a.ptr_off[pA - a.pair_base];
 		const uint32_t t_last = (l2 + 31u) | (JUMP ? 31u : (SPW - 1u));
 		const uint32_t G = t_last / SPW + 1, GJ = (t_last >> 5) + 1;
-		const uint32_t n_stripes = MULTI ? (l1A + RPP - 1) / RPP : 1;
+		constexpr uint32_t n_stripes = 1;
 		uint32_t *__restrict__ ptrJ = ptr + (size_t)n_stripes * G * RPP;
-		int4 *__restrict__ bnd = MULTI ? a.bnd + (size_t)warp_slot * a.bnd_stride : nullptr;
 
 		// ring[(j-1) & 511]: packed (tA << 8) | (tB << 24); int32 (tA << 16) | blacklist bit
 		auto load_block = [&](uint32_t blk) {
@@ -187,8 +183,6 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 			const int cap_r = (!PACKED && last_stripe && lane == (int)(((l1A - 1) % RPP) / R)) ? (int)((l1A - 1) % R) : -1;
 			T kbest = PACKED ? (T)0 : (T)AT_NEG_INIT;     // below every real key
 			T tbest = 0;
-			int4 top_next = make_int4(0, 0, 0, 0);
-			if (MULTI && stripe > 0 && lane == 0) top_next = bnd[1];
 
 			auto step = [&](const uint32_t t, const bool checked) {
 				const int j = (int)t - lane;
@@ -196,15 +190,10 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 				T rL = __shfl_up_sync(0xffffffffu, sL, 1);
 				T rH = __shfl_up_sync(0xffffffffu, sH, 1);
 				T rC = __shfl_up_sync(0xffffffffu, sC, 1);
-				if (lane == 0) {
-					if (!MULTI || stripe == 0) {     // matrix row 0 at column j = t
-						if (MODE == MODE_GLOBAL)     { rM = NEGV; rL = NEGV; rH = V::value(o + e * j) + m8; rC = V::raw(ST_UPP); }   // :437-441
-						else if (MODE == MODE_LOCAL) { rM = ZERO + o8; rL = ZERO; rH = ZERO + m8; rC = V::raw(ST_LOW); }
-						else                         { rM = ZERO + o8; rL = NEGV; rH = ZERO + m8; rC = V::raw(ST_MID); }             // :619-624
-					} else {
-						rM = (T)top_next.x; rL = (T)top_next.y; rH = (T)top_next.z; rC = (T)top_next.w;
-						if (t + 1 <= l2) top_next = bnd[t + 1];
-					}
+				if (lane == 0) {     // matrix row 0 at column j = t
+					if (MODE == MODE_GLOBAL)     { rM = NEGV; rL = NEGV; rH = V::value(o + e * j) + m8; rC = V::raw(ST_UPP); }   // :437-441
+					else if (MODE == MODE_LOCAL) { rM = ZERO + o8; rL = ZERO; rH = ZERO + m8; rC = V::raw(ST_LOW); }
+					else                         { rM = ZERO + o8; rL = NEGV; rH = ZERO + m8; rC = V::raw(ST_MID); }             // :619-624
 				}
 				if (checked && t == 0) { rH = pH; rC = pC; }   // step 0 only primes the pipeline: keep H(row0, 0)
 				T D = pH, DC = pC;
@@ -257,7 +246,6 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 						if (PACKED) { const T chg = V::flag(kbest ^ kold, 1) * 0xffffu; tbest = (tbest & ~chg) | ((T)(t * 0x10001u) & chg); }
 						else if (kbest != kold) tbest = (T)t;
 					}
-					if (MULTI) { if (lane == 31 && !last_stripe) bnd[j] = make_int4((int)sM, (int)sL, (int)sH, (int)sC); }
 				} else {
 #pragma unroll
 					for (int r = 0; r < R; ++r) { acc[r] *= 16u; if (JUMP) accJ[r] *= 2u; }

@@ -1,7 +1,11 @@
 // at_kernels.cuh -- sm_100a device code of the alignTools DP core.
 //
-// K1  at_fill_affine<MODE,R,JUMP>  : Gotoh M/L/U(/J) fill, one pair per warp, int32 lanes.
-//     at_fill_linear<MODE,R>       : single-plane fill (overlap max-plus / edit min-plus).
+// K1  at_fill_affine<MODE,R,JUMP,PACKED> : Gotoh M/L/U(/J) fill of short pairs (l1 <= 256), one pair
+//                                    (or two, packed s16x2) per warp          (at_fill_affine.cuh)
+// K2  at_wave_affine<MODE,JUMP>    : the same recurrences for long pairs: stripes of 256 rows
+//     at_wave_linear<MODE,R>         pipelined over warps / CTAs, TMA-staged target tiles; the
+//                                    single-plane kernel (overlap max-plus / edit min-plus) serves
+//                                    every length                               (at_wavefront.cuh)
 // K3  at_traceback_walk            : device traceback, one thread per pair chases the pointers
 //                                    once and leaves the reversed run-length ops in scratch;
 //     at_traceback_emit            : one warp per pair writes the dense CIGAR and replays it over
@@ -39,132 +43,12 @@ enum { CIG_M = 0, CIG_I = 1, CIG_D = 2, CIG_N = 3 };
 #define AT_NEG (-(1 << 29))
 #define AT_NEG_INIT (-(1 << 30) - (1 << 29))
 
-struct FillArgs {
-	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
-	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
-	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
-	const uint32_t *jobs;    // FillJob records {a, b} (largest pairs first); the single-plane kernels read .a
-	uint32_t        n_jobs;
-	uint32_t       *counter; // dynamic job queue
-	uint32_t       *ptr;     // traceback pointer arena (32-bit words)
-	const uint64_t *ptr_off; // [pair] word offset of the pair's pointer block (chunk-local index)
-	uint32_t        pair_base; // first pair of the chunk (ptr_off is indexed pair - pair_base)
-	int4           *bnd;     // stripe boundary rows, one slab per resident warp
-	uint32_t        bnd_stride;
-	int32_t        *score;   uint32_t *end_i;  uint32_t *end_j;  uint8_t *end_state;
-	int             m, u, o, e, jp;
-	int             want_ptr;
-};
-
 __device__ __forceinline__ uint32_t steps_last(uint32_t l2, int align_mask) { return (l2 + 31u) | (uint32_t)align_mask; }
 
 }  // namespace at
 #include "at_fill_affine.cuh"
+#include "at_wavefront.cuh"
 namespace at {
-
-// ------------------------------------------------------------------------------------
-// Single-plane fill: overlap (src/alignment.h:926-964, linear gap `o`, order
-// LEFT > DIAGONAL > RIGHT, 2-bit pointers, 16 steps per word) and edit distance
-// (:291-315, min-plus, unit gaps, no pointers).
-// ------------------------------------------------------------------------------------
-template <int MODE, int R>
-__device__ __forceinline__ void fill_linear_pair(const FillArgs &a, const uint32_t p, const int lane, const uint32_t warp_slot)
-{
-	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
-	const uint8_t *__restrict__ q  = a.q + a.q_off[p];
-	const uint8_t *__restrict__ tg = a.t + a.t_off[p];
-	uint32_t *__restrict__ ptr = MODE == MODE_OVERLAP ? a.ptr + a.ptr_off[p - a.pair_base] : nullptr;
-	const int m = a.m, u = a.u, o = a.o;
-	constexpr int RPP = 32 * R;
-	const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
-	const uint32_t t_last = steps_last(l2, 15);
-	const uint32_t G = (t_last >> 4) + 1;
-	int4 *__restrict__ bnd = a.bnd + (size_t)warp_slot * a.bnd_stride;
-	const bool want_ptr = a.want_ptr != 0 && MODE == MODE_OVERLAP;
-	int capM = 0, capMj = 0;     // overlap: M[l1][0] = 0 seeds the search (:954-959)
-	int eH = 0;                  // edit: M[l1][l2]
-
-	for (uint32_t stripe = 0; stripe < n_stripes; ++stripe) {
-		const uint32_t row0 = stripe * RPP + lane * R;
-		const bool last_stripe = stripe + 1 == n_stripes;
-		int ac[R], Ml[R];
-		uint32_t acc[R];
-#pragma unroll
-		for (int r = 0; r < R; ++r) {
-			const uint32_t ri = row0 + r;
-			ac[r] = ri < l1 ? (int)q[ri] : 0x100;
-			Ml[r] = MODE == MODE_OVERLAP ? 0 : (int)ri + 1;     // M[i][0] = 0 (:938) | i (:301)
-			acc[r] = 0;
-		}
-		int sM = Ml[R - 1];
-		int pH = MODE == MODE_OVERLAP ? 0 : (int)row0;           // M[row0][0]
-		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
-		int top_next = 0;
-		if (stripe > 0 && lane == 0) top_next = bnd[1].x;
-
-		for (uint32_t t = 1; t <= t_last; ++t) {
-			const int j = (int)t - lane;
-			int rM = __shfl_up_sync(0xffffffffu, sM, 1);
-			if (lane == 0) {
-				if (stripe == 0) rM = MODE == MODE_OVERLAP ? AT_NEG : j;      // M[0][j] = -inf (:937) | j (:302)
-				else { rM = top_next; if (t + 1 <= l2) top_next = bnd[t + 1].x; }
-			}
-			int D = pH;
-			pH = rM;
-			if (j >= 1 && j <= (int)l2) {
-				const int c = (int)__ldg(tg + (j - 1));
-				int Mup = rM, v = 0;
-#pragma unroll
-				for (int r = 0; r < R; ++r) {
-					const bool eq = ac[r] == c;
-					if (MODE == MODE_OVERLAP) {
-						const int left = Ml[r] + o, diag = D + (eq ? m : u), up = Mup + o;
-						v = left; uint32_t code = 1;                       // 1 LEFT, 2 DIAGONAL, 3 RIGHT (0 = never set)
-						if (diag > v) { v = diag; code = 2; }
-						if (up > v)   { v = up;   code = 3; }
-						acc[r] = (acc[r] << 2) | code;
-						if (r == cap_r && j < (int)l2) { if (v > capM) { capM = v; capMj = j; } }
-					} else {
-						const int left = Ml[r] + 1, diag = D + (eq ? 0 : u), up = Mup + 1;
-						v = min(min(left, diag), up);                     // min3 (:280-286)
-						if (r == cap_r && j == (int)l2) eH = v;
-					}
-					D = Ml[r]; Ml[r] = v; Mup = v;
-				}
-				sM = v;
-				if (lane == 31 && !last_stripe) bnd[j].x = sM;
-			} else if (MODE == MODE_OVERLAP) {
-#pragma unroll
-				for (int r = 0; r < R; ++r) acc[r] <<= 2;
-			}
-			if (want_ptr && (t & 15u) == 15u) {
-				uint32_t *w = ptr + ((size_t)(stripe * G + (t >> 4)) * 32 + lane) * R;
-#pragma unroll
-				for (int r = 0; r < R; ++r) w[r] = acc[r];
-			}
-		}
-		__syncwarp();
-	}
-	const int owner = (int)(((l1 - 1) % RPP) / R);
-	if (lane == owner) {
-		if (MODE == MODE_OVERLAP) { a.score[p] = capM; a.end_i[p] = l1; a.end_j[p] = capMj; a.end_state[p] = ST_MID; }
-		else { a.score[p] = eH; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = ST_MID; }
-	}
-}
-
-template <int MODE, int R>
-__global__ void __launch_bounds__(128) at_fill_linear(const FillArgs a)
-{
-	const int lane = threadIdx.x & 31;
-	const uint32_t warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	for (;;) {
-		uint32_t job = 0;
-		if (lane == 0) job = atomicAdd(a.counter, 1u);
-		job = __shfl_sync(0xffffffffu, job, 0);
-		if (job >= a.n_jobs) break;
-		fill_linear_pair<MODE, R>(a, a.jobs[2 * job], lane, warp_slot);   // jobs are FillJob{a,b} records; int32 lanes use .a
-	}
-}
 
 // ------------------------------------------------------------------------------------
 // K3 traceback (reference: trace_back_gla :372-412, trace_back_fit_affine_jump :558-592,
@@ -243,11 +127,11 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 
 	if (a.mode == MODE_OVERLAP) {
 		while (j > 0) {                                   // :899
-			const uint32_t c = pv.two(i, j);
-			if (c == 1)      { --j; w.col(CIG_D); }                  // LEFT
-			else if (c == 2) { --i; --j; w.col(CIG_M); }             // DIAGONAL
-			else if (c == 3) { --i; w.col(CIG_I); }                  // RIGHT
-			else break;                                   // unset pointer: unreachable on a finite path
+			if (i == 0) break;                            // row 0 is -inf (:937): unreachable on a finite path
+			const uint32_t c = pv.two(i, j);              // bit 1: RIGHT beat both; bit 0: DIAGONAL beat LEFT
+			if (c & 2u)      { --i; w.col(CIG_I); }                  // RIGHT
+			else if (c & 1u) { --i; --j; w.col(CIG_M); }             // DIAGONAL
+			else             { --j; w.col(CIG_D); }                  // LEFT
 		}
 	} else {
 		bool home = false;

@@ -135,19 +135,30 @@ template <class T> struct DevBuf {
 };
 
 static const int MAXR = 8;
+static const size_t AT_SEQ_SLACK = 1024;   // K2 stages 256-byte target tiles by TMA: the last tile may run past the last record
+
+// One kernel launch of a chunk: the jobs of one (kernel kind, rows-per-lane) class.
+enum { LK_INT32 = 0, LK_PACKED = 1, LK_WAVE = 2 };
+struct Launch {
+	int kind = LK_INT32, r = 1;
+	uint64_t cells = 0;
+	std::vector<FillJob> h_jobs;        // LK_INT32: one pair per warp (a == b); LK_PACKED: two pairs per warp
+	DevBuf<FillJob> d_jobs;
+	std::vector<WaveTask> h_tasks;      // LK_WAVE: (pair, stripe), pair-major
+	DevBuf<WaveTask> d_tasks;
+	uint64_t prog_base = 0;             // first progress word of this launch in Shard::d_prog
+	size_t n_jobs() const { return kind == LK_WAVE ? h_tasks.size() : h_jobs.size(); }
+};
 
 struct Chunk {
 	uint32_t k0 = 0, k1 = 0;            // shard-local pair range
 	uint64_t ptr_words = 0;
 	std::vector<uint64_t> h_ptr_off;    // chunk-local
 	DevBuf<uint64_t> d_ptr_off;
-	std::vector<FillJob> h_jobs[MAXR + 1];  // int32 lanes: one pair per warp (a == b)
-	DevBuf<FillJob> d_jobs[MAXR + 1];
-	bool multi_r[MAXR + 1] = {false};
-	uint64_t cells_r[MAXR + 1] = {0};
-	std::vector<FillJob> h_jobs2[MAXR + 1]; // packed s16x2 lanes: two pairs per warp
-	DevBuf<FillJob> d_jobs2[MAXR + 1];
-	uint64_t cells_r2[MAXR + 1] = {0};
+	std::vector<Launch> launches;
+	std::vector<uint64_t> h_bnd_off;    // chunk-local: element offset of the pair's two boundary slabs (K2)
+	DevBuf<uint64_t> d_bnd_off;
+	uint64_t bnd_elems = 0, prog_words = 0;
 	DevBuf<uint64_t> d_ops_off, d_cols_off, d_scratch_off;
 	std::vector<uint64_t> h_scratch_off; uint64_t scratch_words = 0;
 	DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_aln1, d_aln2;
@@ -162,10 +173,9 @@ struct Shard {
 	DevBuf<uint64_t> d_q_off, d_t_off, d_site_off;
 	DevBuf<uint32_t> d_q_len, d_t_len, d_end_i, d_end_j, d_beg_i, d_beg_j, d_n_ops, d_n_cols, d_counter;
 	DevBuf<int32_t> d_score, d_sites;
-	DevBuf<uint32_t> d_ptr, d_scratch; DevBuf<int4> d_bnd; DevBuf<uint8_t> d_scan_tmp;
+	DevBuf<uint32_t> d_ptr, d_scratch, d_prog; DevBuf<uint8_t> d_bnd, d_scan_tmp; DevBuf<int32_t> d_chain;
 	std::vector<uint8_t> h_rclass;
 	std::vector<Chunk> chunks;
-	uint32_t max_l2 = 0; bool multi_stripe = false;
 	uint64_t cells = 0, ptr_bytes = 0;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t evk[2] = {nullptr, nullptr};
@@ -229,7 +239,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 	}
 	DevBuf<uint8_t> &raw = encoding == AT_SEQ_2BIT ? d_packed : d_bytes;
 	if (monotonic && hi - lo <= 2 * tot + 64) {          // one bulk copy of the caller's span
-		CU(h, raw.alloc(hi - lo + 16));
+		CU(h, raw.alloc(hi - lo + AT_SEQ_SLACK));
 		CU(h, cudaMemcpyAsync(raw.p, src + lo, hi - lo, cudaMemcpyHostToDevice, st));
 		for (uint32_t k = 0; k < n; ++k) rel[k] = off[s.p0 + k] - lo;
 	} else {                                             // scattered records: repack on the host first
@@ -240,7 +250,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 			rel[k] = pos; stage.resize(pos + nbytes);
 			memcpy(stage.data() + pos, src + off[s.p0 + k], nbytes); pos += nbytes;
 		}
-		CU(h, raw.alloc(pos + 16));
+		CU(h, raw.alloc(pos + AT_SEQ_SLACK));
 		CU(h, cudaMemcpyAsync(raw.p, stage.data(), pos, cudaMemcpyHostToDevice, st));
 		CU(h, cudaStreamSynchronize(st));
 	}
@@ -251,7 +261,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 		CU(h, d_src_off.alloc(n));
 		CU(h, cudaMemcpyAsync(d_src_off.p, rel.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 		CU(h, cudaMemcpyAsync(d_off.p, unp.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-		CU(h, d_bytes.alloc(tot + 16));
+		CU(h, d_bytes.alloc(tot + AT_SEQ_SLACK));
 		at_unpack_2bit<<<n, 128, 0, st>>>(d_packed.p, d_src_off.p, d_off.p, d_len.p, n, d_bytes.p);
 		CU(h, cudaGetLastError());
 		h->launches++;
@@ -273,8 +283,9 @@ static void free_shard(Shard &s)
 	s.d_q_len.release(); s.d_t_len.release(); s.d_end_i.release(); s.d_end_j.release(); s.d_beg_i.release();
 	s.d_beg_j.release(); s.d_n_ops.release(); s.d_n_cols.release(); s.d_counter.release();
 	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_scratch.release(); s.d_bnd.release(); s.d_scan_tmp.release();
+	s.d_prog.release(); s.d_chain.release();
 	for (auto &c : s.chunks) {
-		c.d_ptr_off.release(); for (auto &j : c.d_jobs) j.release(); for (auto &j : c.d_jobs2) j.release();
+		c.d_ptr_off.release(); c.d_bnd_off.release(); for (auto &l : c.launches) { l.d_jobs.release(); l.d_tasks.release(); }
 		c.d_ops_off.release(); c.d_cols_off.release(); c.d_scratch_off.release(); c.d_cigar.release(); c.d_aln1.release(); c.d_aln2.release();
 	}
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
@@ -321,12 +332,10 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	}
 	// per-pair class, result arrays
 	s.h_rclass.resize(n);
-	s.max_l2 = 0; s.multi_stripe = false; s.cells = 0;
+	s.cells = 0;
 	for (uint32_t k = 0; k < n; ++k) {
 		const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
 		s.h_rclass[k] = (uint8_t)rclass_of(l1);
-		s.max_l2 = std::max(s.max_l2, l2);
-		if (l1 > 32u * MAXR) s.multi_stripe = true;
 		s.cells += (uint64_t)l1 * l2;
 	}
 	CU(h, s.d_score.alloc(n)); CU(h, s.d_end_i.alloc(n)); CU(h, s.d_end_j.alloc(n)); CU(h, s.d_end_state.alloc(n));
@@ -374,16 +383,26 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		cur.k1 = n; s.chunks.push_back(std::move(cur));
 	}
 	s.ptr_bytes = 0;
+	const bool linear = b->mode >= AT_OVERLAP;          // single-plane modes run on K2 at every length
+	uint64_t max_bnd_elems = 0, max_prog_words = 0;
 	for (auto &c : s.chunks) {
 		const uint32_t nc = c.k1 - c.k0;
 		auto cells_of = [&](uint32_t k) { return (uint64_t)in->q_len[s.p0 + k] * in->t_len[s.p0 + k]; };
-		// ---- packed jobs: partners must share the rows-per-lane class and l2 ----
-		std::vector<uint32_t> scalar_pairs;
+		auto by_cells = [&](std::vector<uint32_t> &v) {   // largest pairs first (dynamic queue => good tail balance)
+			bool ragged = false;
+			for (size_t x = 1; x < v.size() && !ragged; ++x) ragged = cells_of(v[x]) != cells_of(v[0]);
+			if (ragged) std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) { return cells_of(x) > cells_of(y); });
+		};
+		Launch l32[MAXR + 1], l16[MAXR + 1], lwv[MAXR + 1];
+		std::vector<uint32_t> scalar_pairs, wave_pairs, cand;
+		for (uint32_t k = c.k0; k < c.k1; ++k) {
+			const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
+			if (linear || l1 > 32u * MAXR) wave_pairs.push_back(k);
+			else if (p16_ok(l1, l2)) cand.push_back(k);
+			else scalar_pairs.push_back(k);
+		}
+		// ---- packed jobs (K1, s16x2): partners must share the rows-per-lane class and l2 ----
 		{
-			std::vector<uint32_t> cand;
-			for (uint32_t k = c.k0; k < c.k1; ++k) {
-				if (p16_ok(in->q_len[s.p0 + k], in->t_len[s.p0 + k])) cand.push_back(k); else scalar_pairs.push_back(k);
-			}
 			auto key = [&](uint32_t k) { return ((uint64_t)s.h_rclass[k] << 32) | in->t_len[s.p0 + k]; };
 			bool sorted = true;
 			for (size_t x = 1; x < cand.size() && sorted; ++x) sorted = key(cand[x - 1]) >= key(cand[x]);
@@ -391,48 +410,72 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 			for (size_t x = 0; x < cand.size();) {
 				if (x + 1 < cand.size() && key(cand[x]) == key(cand[x + 1])) {
 					const int r = s.h_rclass[cand[x]] & 15;
-					c.h_jobs2[r].push_back(FillJob{cand[x], cand[x + 1]});
-					c.cells_r2[r] += cells_of(cand[x]) + cells_of(cand[x + 1]);
+					l16[r].h_jobs.push_back(FillJob{cand[x], cand[x + 1]});
+					l16[r].cells += cells_of(cand[x]) + cells_of(cand[x + 1]);
 					x += 2;
 				} else { scalar_pairs.push_back(cand[x]); x += 1; }
 			}
 		}
-		// ---- int32 jobs per R class, largest pairs first (dynamic queue => good tail balance) ----
-		{
-			bool ragged = false;
-			for (size_t x = 1; x < scalar_pairs.size() && !ragged; ++x) ragged = cells_of(scalar_pairs[x]) != cells_of(scalar_pairs[0]);
-			if (ragged) std::stable_sort(scalar_pairs.begin(), scalar_pairs.end(), [&](uint32_t x, uint32_t y) { return cells_of(x) > cells_of(y); });
-			for (uint32_t k : scalar_pairs) { const int r = s.h_rclass[k] & 15; c.h_jobs[r].push_back(FillJob{k, k}); c.cells_r[r] += cells_of(k); if (in->q_len[s.p0 + k] > 32u * MAXR) c.multi_r[r] = true; }
+		// ---- int32 jobs (K1) per R class ----
+		by_cells(scalar_pairs);
+		for (uint32_t k : scalar_pairs) { const int r = s.h_rclass[k] & 15; l32[r].h_jobs.push_back(FillJob{k, k}); l32[r].cells += cells_of(k); }
+		// ---- wavefront tasks (K2): (pair, stripe), pair-major so that a stripe's predecessor is the task before it ----
+		by_cells(wave_pairs);
+		c.h_bnd_off.assign(nc, 0);
+		c.bnd_elems = 0; c.prog_words = 0;
+		for (uint32_t k : wave_pairs) {
+			const int r = s.h_rclass[k] & 15;
+			const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
+			const uint32_t n_stripes = (l1 + 32u * r - 1) / (32u * r);
+			for (uint32_t st2 = 0; st2 < n_stripes; ++st2) lwv[r].h_tasks.push_back(WaveTask{k, st2});
+			lwv[r].cells += cells_of(k);
+			if (n_stripes > 1) { c.h_bnd_off[k - c.k0] = c.bnd_elems; c.bnd_elems += 2ull * ((l2 + 4u) & ~3u); }
 		}
-		// ---- pointer blocks: one per int32 pair, one per packed job (shared by its two pairs) ----
+		for (int r = 1; r <= MAXR; ++r) {
+			if (!l32[r].h_jobs.empty()) { l32[r].kind = LK_INT32; l32[r].r = r; c.launches.push_back(std::move(l32[r])); }
+			if (!l16[r].h_jobs.empty()) { l16[r].kind = LK_PACKED; l16[r].r = r; c.launches.push_back(std::move(l16[r])); }
+			if (!lwv[r].h_tasks.empty()) {
+				lwv[r].kind = LK_WAVE; lwv[r].r = r; lwv[r].prog_base = c.prog_words; c.prog_words += lwv[r].h_tasks.size();
+				c.launches.push_back(std::move(lwv[r]));
+			}
+		}
+		max_bnd_elems = std::max(max_bnd_elems, c.bnd_elems);
+		max_prog_words = std::max(max_prog_words, c.prog_words);
+		// ---- pointer blocks: one per int32 / wavefront pair, one per packed job (shared by its two pairs) ----
 		c.h_ptr_off.assign(nc, 0);
 		uint64_t words = 0;
 		if (b->traceback) {
-			for (int r = 1; r <= MAXR; ++r) {
-				for (const FillJob &jb : c.h_jobs[r]) { const uint32_t k = jb.a; c.h_ptr_off[k - c.k0] = words; words += ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]); }
-				for (const FillJob &jb : c.h_jobs2[r]) {
-					const uint32_t tl = (in->t_len[s.p0 + jb.a] + 31u) | 3u;
-					c.h_ptr_off[jb.a - c.k0] = words; c.h_ptr_off[jb.b - c.k0] = words;
-					s.h_rclass[jb.a] = (uint8_t)(r | (1 << 4)); s.h_rclass[jb.b] = (uint8_t)(r | (2 << 4));
-					words += (uint64_t)((tl >> 2) + 1) * r * 32;
+			for (const Launch &l : c.launches) {
+				if (l.kind == LK_PACKED) {
+					for (const FillJob &jb : l.h_jobs) {
+						const uint32_t tl = (in->t_len[s.p0 + jb.a] + 31u) | 3u;
+						c.h_ptr_off[jb.a - c.k0] = words; c.h_ptr_off[jb.b - c.k0] = words;
+						s.h_rclass[jb.a] = (uint8_t)(l.r | (1 << 4)); s.h_rclass[jb.b] = (uint8_t)(l.r | (2 << 4));
+						words += (uint64_t)((tl >> 2) + 1) * l.r * 32;
+					}
+				} else if (l.kind == LK_INT32) {
+					for (const FillJob &jb : l.h_jobs) { const uint32_t k = jb.a; c.h_ptr_off[k - c.k0] = words; words += ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]); }
+				} else {
+					for (const WaveTask &tk : l.h_tasks) if (tk.stripe == 0) { const uint32_t k = tk.pair; c.h_ptr_off[k - c.k0] = words; words += ptr_words_of(b->mode, jump, in->q_len[s.p0 + k], in->t_len[s.p0 + k]); }
 				}
 			}
 		}
 		c.ptr_words = words;
 		max_chunk_words = std::max(max_chunk_words, c.ptr_words);
 		s.ptr_bytes += c.ptr_words * 4;
-		for (int r = 1; r <= MAXR; ++r) {
-			if (!c.h_jobs[r].empty()) {
-				CU(h, c.d_jobs[r].alloc(c.h_jobs[r].size()));
-				CU(h, cudaMemcpyAsync(c.d_jobs[r].p, c.h_jobs[r].data(), c.h_jobs[r].size() * sizeof(FillJob), cudaMemcpyHostToDevice, st));
-			}
-			if (!c.h_jobs2[r].empty()) {
-				CU(h, c.d_jobs2[r].alloc(c.h_jobs2[r].size()));
-				CU(h, cudaMemcpyAsync(c.d_jobs2[r].p, c.h_jobs2[r].data(), c.h_jobs2[r].size() * sizeof(FillJob), cudaMemcpyHostToDevice, st));
+		for (Launch &l : c.launches) {
+			if (l.kind == LK_WAVE) {
+				CU(h, l.d_tasks.alloc(l.h_tasks.size()));
+				CU(h, cudaMemcpyAsync(l.d_tasks.p, l.h_tasks.data(), l.h_tasks.size() * sizeof(WaveTask), cudaMemcpyHostToDevice, st));
+			} else {
+				CU(h, l.d_jobs.alloc(l.h_jobs.size()));
+				CU(h, cudaMemcpyAsync(l.d_jobs.p, l.h_jobs.data(), l.h_jobs.size() * sizeof(FillJob), cudaMemcpyHostToDevice, st));
 			}
 		}
 		CU(h, c.d_ptr_off.alloc(nc));
 		CU(h, cudaMemcpyAsync(c.d_ptr_off.p, c.h_ptr_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		CU(h, c.d_bnd_off.alloc(nc));
+		CU(h, cudaMemcpyAsync(c.d_bnd_off.p, c.h_bnd_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 		if (b->traceback) {
 			CU(h, c.d_ops_off.alloc(nc + 1)); CU(h, c.d_cols_off.alloc(nc + 1));
 			// traceback scratch: a slot of l1+l2 run-length ops per pair (an alignment has at most l1+l2 columns)
@@ -445,6 +488,14 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 			CU(h, cudaMemcpyAsync(c.d_scratch_off.p, c.h_scratch_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 		}
 		CU(h, cudaStreamSynchronize(st));
+	}
+	if (max_bnd_elems && s.d_bnd.alloc(max_bnd_elems * (linear ? sizeof(int32_t) : sizeof(int4)) + 64) != cudaSuccess) { set_err(h, "stripe boundary slabs of %llu MB", (unsigned long long)((max_bnd_elems * (linear ? 4 : 16)) >> 20)); return AT_E_NOMEM; }
+	if (!max_bnd_elems) CU(h, s.d_bnd.alloc(64));
+	CU(h, s.d_prog.alloc(max_prog_words + 1));
+	{
+		uint32_t max_nc = 0;
+		for (auto &c : s.chunks) max_nc = std::max(max_nc, c.k1 - c.k0);
+		CU(h, s.d_chain.alloc(4ull * max_nc + 4));
 	}
 	if (max_scratch_words && s.d_scratch.alloc(max_scratch_words) != cudaSuccess) { set_err(h, "traceback scratch of %llu MB", (unsigned long long)(max_scratch_words >> 18)); return AT_E_NOMEM; }
 	CU(h, s.d_rclass.alloc(n));
@@ -510,43 +561,46 @@ extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const
 }
 
 // ------------------------------------------------------------------ launch ----
-// Kernel table: mode variant x rows-per-lane x lanes.  kind: 0 global, 1 local, 2 fit, 3 fit+jump
-// (int32 lanes, optionally multi-stripe for R = 8), 4 local on packed s16x2 lanes, 5 overlap, 6 edit.
+// Kernel tables.  K1 (at_fill_affine): mode variant x rows-per-lane x lanes; kind: 0 global, 1 local,
+// 2 fit, 3 fit+jump on int32 lanes, 4 local on packed s16x2 lanes.  K2 (at_wave_*): affine modes
+// with R = 8, single-plane modes (overlap / edit) with R = 1..8.
 typedef void (*fill2_fn)(const FillArgs2);
-typedef void (*fill1_fn)(const FillArgs);
+typedef void (*wave_fn)(const WaveArgs);
 
-template <int R> static fill2_fn affine_fn(int kind, bool multi)
+template <int R> static fill2_fn affine_fn(int kind)
 {
-	if (multi) {
-		switch (kind) {
-		case 0: return at_fill_affine<MODE_GLOBAL, 8, false, false, true>;
-		case 1: return at_fill_affine<MODE_LOCAL, 8, false, false, true>;
-		case 2: return at_fill_affine<MODE_FIT, 8, false, false, true>;
-		default: return at_fill_affine<MODE_FIT, 8, true, false, true>;
-		}
-	}
 	switch (kind) {
-	case 0: return at_fill_affine<MODE_GLOBAL, R, false, false, false>;
-	case 1: return at_fill_affine<MODE_LOCAL, R, false, false, false>;
-	case 2: return at_fill_affine<MODE_FIT, R, false, false, false>;
-	case 3: return at_fill_affine<MODE_FIT, R, true, false, false>;
-	default: return at_fill_affine<MODE_LOCAL, R, false, true, false>;
+	case 0: return at_fill_affine<MODE_GLOBAL, R, false, false>;
+	case 1: return at_fill_affine<MODE_LOCAL, R, false, false>;
+	case 2: return at_fill_affine<MODE_FIT, R, false, false>;
+	case 3: return at_fill_affine<MODE_FIT, R, true, false>;
+	default: return at_fill_affine<MODE_LOCAL, R, false, true>;
 	}
 }
-static fill2_fn affine_kernel(int kind, int R, bool multi)
+static fill2_fn affine_kernel(int kind, int R)
 {
 	switch (R) {
-	case 1: return affine_fn<1>(kind, multi); case 2: return affine_fn<2>(kind, multi); case 3: return affine_fn<3>(kind, multi);
-	case 4: return affine_fn<4>(kind, multi); case 5: return affine_fn<5>(kind, multi); case 6: return affine_fn<6>(kind, multi);
-	case 7: return affine_fn<7>(kind, multi); default: return affine_fn<8>(kind, multi);
+	case 1: return affine_fn<1>(kind); case 2: return affine_fn<2>(kind); case 3: return affine_fn<3>(kind);
+	case 4: return affine_fn<4>(kind); case 5: return affine_fn<5>(kind); case 6: return affine_fn<6>(kind);
+	case 7: return affine_fn<7>(kind); default: return affine_fn<8>(kind);
 	}
 }
-template <int MODE> static fill1_fn linear_fn(int R)
+template <int MODE> static wave_fn wave_linear_fn(int R)
 {
 	switch (R) {
-	case 1: return at_fill_linear<MODE, 1>; case 2: return at_fill_linear<MODE, 2>; case 3: return at_fill_linear<MODE, 3>;
-	case 4: return at_fill_linear<MODE, 4>; case 5: return at_fill_linear<MODE, 5>; case 6: return at_fill_linear<MODE, 6>;
-	case 7: return at_fill_linear<MODE, 7>; default: return at_fill_linear<MODE, 8>;
+	case 1: return at_wave_linear<MODE, 1>; case 2: return at_wave_linear<MODE, 2>; case 3: return at_wave_linear<MODE, 3>;
+	case 4: return at_wave_linear<MODE, 4>; case 5: return at_wave_linear<MODE, 5>; case 6: return at_wave_linear<MODE, 6>;
+	case 7: return at_wave_linear<MODE, 7>; default: return at_wave_linear<MODE, 8>;
+	}
+}
+static wave_fn wave_kernel(int mode, bool jump, int R)
+{
+	switch (mode) {
+	case AT_GLOBAL: return at_wave_affine<MODE_GLOBAL, false>;
+	case AT_LOCAL: return at_wave_affine<MODE_LOCAL, false>;
+	case AT_FIT: return jump ? at_wave_affine<MODE_FIT, true> : at_wave_affine<MODE_FIT, false>;
+	case AT_OVERLAP: return wave_linear_fn<MODE_OVERLAP>(R);
+	default: return wave_linear_fn<MODE_EDIT>(R);
 	}
 }
 
@@ -561,12 +615,10 @@ static int run_shard(at_batch *b, Shard &s)
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
 	s.fill_ms = s.tb_ms = s.dev_ms = s.domk_ms = 0; s.domk_cells = 0; s.launches = 0;
 	// dominant (most cells) fill launch of the whole shard -> per-launch timing for the roofline
-	int dom_chunk = -1, dom_r = -1; uint64_t dom_cells = 0;
+	int dom_chunk = -1, dom_launch = -1; uint64_t dom_cells = 0;
 	for (size_t ci = 0; ci < s.chunks.size(); ++ci)
-		for (int r = 1; r <= MAXR; ++r) {
-			if (s.chunks[ci].cells_r[r] > dom_cells) { dom_cells = s.chunks[ci].cells_r[r]; dom_chunk = (int)ci; dom_r = r; }
-			if (s.chunks[ci].cells_r2[r] > dom_cells) { dom_cells = s.chunks[ci].cells_r2[r]; dom_chunk = (int)ci; dom_r = r + 100; }
-		}
+		for (size_t li = 0; li < s.chunks[ci].launches.size(); ++li)
+			if (s.chunks[ci].launches[li].cells > dom_cells) { dom_cells = s.chunks[ci].launches[li].cells; dom_chunk = (int)ci; dom_launch = (int)li; }
 
 	cudaEvent_t e_begin = s.ev[0], e_fill = s.ev[1], e_tb = s.ev[2];
 	float ms = 0;
@@ -576,57 +628,48 @@ static int run_shard(at_batch *b, Shard &s)
 		Chunk &c = s.chunks[ci];
 		const uint32_t nc = c.k1 - c.k0;
 		CU(h, cudaMemsetAsync(s.d_counter.p, 0, 64 * sizeof(uint32_t), st));
+		if (c.prog_words) CU(h, cudaMemsetAsync(s.d_prog.p, 0, c.prog_words * sizeof(uint32_t), st));
 		CU(h, cudaEventRecord(e_begin, st));
 		if (first) { CU(h, cudaEventRecord(e_first, st)); first = false; }
-		for (int pass = 0; pass < 2; ++pass) {      // pass 0: int32 lanes, pass 1: packed s16x2 lanes
-			for (int r = 1; r <= MAXR; ++r) {
-				std::vector<FillJob> &hj = pass ? c.h_jobs2[r] : c.h_jobs[r];
-				if (hj.empty()) continue;
-				const bool affine = b->mode <= AT_FIT;
-				const bool multi = !pass && c.multi_r[r];
-				const int kind = pass ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode);
-				const void *fn = affine ? (const void *)affine_kernel(kind, r, multi)
-				                        : (b->mode == AT_OVERLAP ? (const void *)linear_fn<MODE_OVERLAP>(r) : (const void *)linear_fn<MODE_EDIT>(r));
-				int occ = 0;
-				CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * AT_FILL_WARPS, 0));
-				if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, r); return AT_E_CUDA; }
-				int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (hj.size() + AT_FILL_WARPS - 1) / AT_FILL_WARPS);
-				if (blocks < 1) blocks = 1;
-				const bool need_bnd = multi || (!affine && c.multi_r[r]);
-				if (need_bnd) {     // one boundary slab per resident warp
-					const uint64_t stride = (uint64_t)s.max_l2 + 2;
-					if (s.d_bnd.alloc((size_t)blocks * AT_FILL_WARPS * stride) != cudaSuccess) { set_err(h, "stripe boundary slabs"); return AT_E_NOMEM; }
-				} else CU(h, s.d_bnd.alloc(1));
-				const bool dom = (int)ci == dom_chunk && (pass ? r + 100 : r) == dom_r;
-				if (dom) CU(h, cudaEventRecord(s.evk[0], st));
-				if (affine) {
-					FillArgs2 fa;
-					fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
-					fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
-					fa.jmask = s.d_jmask.p; fa.jobs = pass ? c.d_jobs2[r].p : c.d_jobs[r].p; fa.n_jobs = (uint32_t)hj.size();
-					fa.counter = s.d_counter.p + (pass ? 16 : 0) + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
-					fa.bnd = s.d_bnd.p; fa.bnd_stride = s.max_l2 + 2;
-					fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
-					fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
-					fa.want_ptr = b->traceback ? 1 : 0;
-					void *kargs[] = {(void *)&fa};
-					CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * AT_FILL_WARPS), kargs, 0, st));
-				} else {
-					FillArgs fa;
-					fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
-					fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
-					fa.jmask = nullptr; fa.jobs = (const uint32_t *)c.d_jobs[r].p; fa.n_jobs = (uint32_t)hj.size();
-					fa.counter = s.d_counter.p + r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
-					fa.bnd = s.d_bnd.p; fa.bnd_stride = s.max_l2 + 2;
-					fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
-					fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
-					fa.want_ptr = b->traceback ? 1 : 0;
-					void *kargs[] = {(void *)&fa};
-					CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * AT_FILL_WARPS), kargs, 0, st));
-				}
-				if (dom) CU(h, cudaEventRecord(s.evk[1], st));
-				s.launches++;
+		for (size_t li = 0; li < c.launches.size(); ++li) {
+			Launch &l = c.launches[li];
+			const void *fn = l.kind == LK_WAVE ? (const void *)wave_kernel(b->mode, jump, l.r)
+			                                   : (const void *)affine_kernel(l.kind == LK_PACKED ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode), l.r);
+			const int warps = l.kind == LK_WAVE ? AT_WAVE_WARPS : AT_FILL_WARPS;
+			int occ = 0;
+			CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * warps, 0));
+			if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, l.r); return AT_E_CUDA; }
+			int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (l.n_jobs() + warps - 1) / warps);
+			if (blocks < 1) blocks = 1;
+			const bool dom = (int)ci == dom_chunk && (int)li == dom_launch;
+			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
+			if (l.kind == LK_WAVE) {
+				WaveArgs wa;
+				wa.q = s.d_q.p; wa.q_off = s.d_q_off.p; wa.q_len = s.d_q_len.p;
+				wa.t = s.d_t.p; wa.t_off = s.d_t_off.p; wa.t_len = s.d_t_len.p;
+				wa.jmask = s.d_jmask.p; wa.tasks = l.d_tasks.p; wa.n_tasks = (uint32_t)l.h_tasks.size();
+				wa.counter = s.d_counter.p + 32 + l.r; wa.prog = s.d_prog.p + l.prog_base;
+				wa.ptr = s.d_ptr.p; wa.ptr_off = c.d_ptr_off.p; wa.pair_base = c.k0;
+				wa.bnd = s.d_bnd.p; wa.bnd_off = c.d_bnd_off.p; wa.chain = s.d_chain.p;
+				wa.score = s.d_score.p; wa.end_i = s.d_end_i.p; wa.end_j = s.d_end_j.p; wa.end_state = s.d_end_state.p;
+				wa.m = b->prm.m; wa.u = b->prm.u; wa.o = b->prm.o; wa.e = b->prm.e; wa.jp = b->prm.j;
+				wa.want_ptr = b->traceback ? 1 : 0;
+				void *kargs[] = {(void *)&wa};
+				CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warps), kargs, 0, st));
+			} else {
+				FillArgs2 fa;
+				fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
+				fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
+				fa.jmask = s.d_jmask.p; fa.jobs = l.d_jobs.p; fa.n_jobs = (uint32_t)l.h_jobs.size();
+				fa.counter = s.d_counter.p + (l.kind == LK_PACKED ? 16 : 0) + l.r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
+				fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
+				fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
+				fa.want_ptr = b->traceback ? 1 : 0;
+				void *kargs[] = {(void *)&fa};
+				CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warps), kargs, 0, st));
 			}
+			if (dom) CU(h, cudaEventRecord(s.evk[1], st));
+			s.launches++;
 		}
 		CU(h, cudaEventRecord(e_fill, st));
 		if (b->traceback) {

@@ -1,0 +1,568 @@
+// at_wavefront.cuh -- K2: intra-pair anti-diagonal wavefront fill for long sequences, sm_100a.
+// (included by at_kernels.cuh after the constants)
+//
+// A pair is cut into STRIPES of 32*R rows.  Every (pair, stripe) is a task; the persistent grid
+// claims tasks IN ORDER from an atomic queue, one warp per task, so the stripes of one pair run
+// concurrently on different warps / CTAs / SMs, each lagging its predecessor by three 32-column
+// blocks: the warps of a pair sit on an anti-diagonal of (stripe, column-block) tiles.  Inside a
+// stripe the warp is the same systolic array as K1 (lane k owns R rows, column j = t - k).
+//
+//   * target tiles (and the jump blacklist) are staged by TMA: one elected lane issues
+//     cp.async.bulk global -> shared for the next 256-column tile into a two-slot ring and the
+//     warp waits on the slot's mbarrier just before the first lane enters the tile;
+//   * the last row of a stripe (lane 31) is parked in a shared-memory stage, flushed 32 columns
+//     at a time with one coalesced store to the pair's boundary slab (L2 resident, two slabs
+//     alternating by stripe parity) and published with a release of the task's progress word;
+//   * the next stripe polls that word (acquire), pulls the 32-column block with one coalesced
+//     ld.global.cg a block ahead of its use and feeds lane 0 from a shared-memory ring;
+//   * traceback pointers go to HBM exactly as in K1 (nibbles / 2-bit codes in skewed coordinates,
+//     one dense 128*R-byte run per warp flush), so K3 walks both kernels' output.
+//
+// Deadlock freedom: tasks are claimed in queue order by warps that are all resident (grid =
+// occupancy x SMs), a warp only ever waits for the task claimed immediately before its own, and
+// stripe 0 of a pair waits for nothing.
+//
+// Reference recurrences: src/alignment.h:451-462 (global), :635-667 (fit), :825-841 (local),
+// :940-949 (overlap), :303-311 (edit); tie rules SURVEY.md A.0.
+#pragma once
+
+namespace at {
+
+#define AT_WAVE_WARPS 4
+#define AT_PROG_DONE 0xffffffffu
+#define AT_NEGL (-(1 << 30))       // -inf stand-in of the single-plane kernel (scores x4 stay below 2^29)
+
+struct WaveTask { uint32_t pair, stripe; };
+
+struct WaveArgs {
+	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
+	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
+	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
+	const WaveTask *tasks;   // pair-major, stripes ascending
+	uint32_t        n_tasks;
+	uint32_t       *counter; // task queue head
+	uint32_t       *prog;    // [n_tasks] columns of the task's last row that are visible in its slab
+	uint32_t       *ptr;     const uint64_t *ptr_off;   uint32_t pair_base;
+	void           *bnd;     // boundary slabs: int4 (affine) or int32 (single plane) per column
+	const uint64_t *bnd_off; // [pair - pair_base] element offset of the pair's two slabs
+	int32_t        *chain;   // [pair - pair_base][4] local mode: best (score, row, column) of the stripes so far
+	int32_t        *score;   uint32_t *end_i;  uint32_t *end_j;  uint8_t *end_state;
+	int             m, u, o, e, jp;
+	int             want_ptr;
+};
+
+// ---- TMA (bulk async copy) + mbarrier + release/acquire helpers ----
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Per-warp target ring: two 256-byte slots per plane, slot c & 1 holds tile c of the target
+// (bytes base + 256*c .. +255 where base is the pair's target address rounded DOWN to 16 bytes,
+// as cp.async.bulk wants; `sh` = the rounding, so target index x lives at ring[(x + sh) & 511]).
+template <bool JUMP> struct __align__(16) WaveRing {
+	uint8_t  tring[512];
+	uint8_t  jring[JUMP ? 512 : 16];
+	uint64_t bar[2];
+};
+
+template <bool JUMP>
+__device__ __forceinline__ void ring_issue(WaveRing<JUMP> &rg, const uint8_t *tbase16, const uint8_t *jbase16, uint32_t c, int lane)
+{
+	if (lane == 0) {
+		fence_proxy_async_smem();      // the slot's previous contents were read through the generic proxy
+		uint64_t *bar = &rg.bar[c & 1];
+		mbar_expect_tx(bar, JUMP ? 512u : 256u);
+		tma_load_1d(rg.tring + 256u * (c & 1), tbase16 + 256ull * c, 256u, bar);
+		if (JUMP) tma_load_1d(rg.jring + 256u * (c & 1), jbase16 + 256ull * c, 256u, bar);
+	}
+}
+
+// Wait until the predecessor task has published column `need` (warp-uniform; `seen` caches the last value read).
+__device__ __forceinline__ void wait_columns(const uint32_t *prog, uint32_t need, uint32_t &seen, int lane)
+{
+	if (seen >= need) return;
+	uint32_t v = 0;
+	if (lane == 0) {
+		v = ld_acquire(prog);
+		while (v < need) { __nanosleep(100); v = ld_acquire(prog); }
+	}
+	seen = __shfl_sync(0xffffffffu, v, 0);
+	__syncwarp();                              // orders the other lanes' loads after lane 0's acquire
+}
+
+// =====================================================================================
+// Affine kernel: global / local / fit (+jump), int32 lanes, R = 8 rows per lane.
+// =====================================================================================
+template <int MODE, bool JUMP>
+__global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveArgs a)
+{
+	constexpr int R = 8, RPP = 32 * R;
+	struct __align__(16) Smem { WaveRing<JUMP> rg; int4 cring[64]; int4 stage[64]; };
+	__shared__ Smem sm_all[AT_WAVE_WARPS];
+	Smem &sm = sm_all[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	if (lane == 0) { mbar_init(&sm.rg.bar[0], 1); mbar_init(&sm.rg.bar[1], 1); fence_proxy_async_smem(); }
+	__syncwarp();
+	uint32_t ring_par = 0;      // bit s: parity of the next completion of slot s's mbarrier
+
+	const int m = a.m, u = a.u, o = a.o, e = a.e;
+	const int m8 = 8 * m, o8 = 8 * o, e8 = 8 * e;
+	const uint32_t mu8 = (uint32_t)(8 * (m >= u ? m - u : u - m));
+	const int nsg = m >= u ? -1 : 1;
+	const int ZERO = 0, NEGV = AT_NEG;
+	const bool want_ptr = a.want_ptr != 0;
+
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0) job = atomicAdd(a.counter, 1u);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= a.n_tasks) break;
+		const WaveTask tk = a.tasks[job];
+		const uint32_t p = tk.pair, stripe = tk.stripe;
+		const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
+		const uint8_t *__restrict__ q = a.q + a.q_off[p];
+		const uint8_t *tbase = a.t + a.t_off[p];
+		const uint32_t sh = (uint32_t)((uintptr_t)tbase & 15u);
+		const uint8_t *tbase16 = tbase - sh;
+		const uint8_t *jbase16 = JUMP ? a.jmask + a.t_off[p] - sh : nullptr;     // jmask and t share their layout (and alignment)
+		const uint32_t n_tiles = (l2 + sh + 255u) >> 8;
+		uint32_t *__restrict__ ptr = a.ptr + a.ptr_off[p - a.pair_base];
+		const uint32_t t_ptr_last = (l2 + 31u) | (JUMP ? 31u : 7u);       // pointer-block geometry shared with K1 / K3
+		const uint32_t G = (t_ptr_last >> 3) + 1, GJ = (t_ptr_last >> 5) + 1;
+		const uint32_t t_last = (l2 + 31u) | 31u;
+		const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
+		uint32_t *__restrict__ ptrJ = ptr + (size_t)n_stripes * G * RPP;
+		const bool last_stripe = stripe + 1 == n_stripes;
+		const uint32_t slab = (l2 + 4u) & ~3u;
+		int4 *bnd_pair = (int4 *)a.bnd + a.bnd_off[p - a.pair_base];
+		int4 *bnd_out = bnd_pair + (size_t)(stripe & 1u) * slab;
+		const int4 *bnd_in = bnd_pair + (size_t)((stripe & 1u) ^ 1u) * slab;
+		const uint32_t *prog_in = a.prog + (stripe ? job - 1 : job);
+		uint32_t seen = 0;
+		const uint32_t row0 = stripe * RPP + lane * R;
+
+		__syncwarp();
+		if (n_tiles > 0) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 0, lane);
+		if (n_tiles > 1) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 1, lane);
+
+		int Mol[R], Ul[R], Hl[R], Cl[R], Jl[R], crow[R];
+		uint32_t ac[R], acc[R], accJ[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const uint32_t ri = row0 + r;
+			const int i = (int)ri + 1;
+			ac[r] = ri < l1 ? ((uint32_t)q[ri] << 16) : 0x4u;
+			crow[r] = ri < l1 ? 7 - r : -(1 << 28);
+			if (MODE == MODE_GLOBAL)     { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = 8 * (o + e * i) + m8; Cl[r] = ST_LOW; }      // :432-436
+			else if (MODE == MODE_LOCAL) { Mol[r] = ZERO + o8; Ul[r] = ZERO; Hl[r] = ZERO + m8; Cl[r] = ST_LOW; }           // calloc zeros
+			else                         { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = NEGV; Cl[r] = ST_MID; }                     // :612-617
+			Jl[r] = NEGV; acc[r] = 0; accJ[r] = 0;
+		}
+		int sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
+		int sL = MODE == MODE_GLOBAL ? 8 * (o + e * (int)(row0 + R)) : (MODE == MODE_LOCAL ? ZERO : NEGV);
+		int pH, pC;      // H(row0, 0) + m and its code: the row above this lane's strip, column 0
+		if (row0 == 0) {
+			if (MODE == MODE_GLOBAL)     { pH = 8 * (o < 0 ? 0 : o) + m8; pC = o < 0 ? ST_MID : ST_LOW; }                    // max5(L=o, M=0, U=o)
+			else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = ST_LOW; }
+			else                         { pH = ZERO + m8; pC = ST_MID; }                                                    // M[0][0]=U[0][0]=0
+		} else {
+			if (MODE == MODE_GLOBAL)     { pH = 8 * (o + e * (int)row0) + m8; pC = ST_LOW; }
+			else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = ST_LOW; }
+			else                         { pH = NEGV; pC = ST_MID; }
+		}
+		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
+		int kbest = AT_NEG_INIT, tbest = 0;                                         // local
+		int capM = AT_NEG_INIT, capMj = 0, capL = AT_NEG_INIT, capLj = 0;           // fit
+		int gH = 0, gC = 0;                                                         // global
+
+		// first boundary block of the stripe above
+		int4 pre = make_int4(0, 0, 0, 0);
+		if (stripe) {
+			wait_columns(prog_in, min(l2, 31u), seen, lane);
+			if ((uint32_t)lane <= l2) pre = __ldcg(bnd_in + lane);
+		}
+		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
+
+		auto step = [&](const uint32_t t, const bool checked) {
+			const int j = (int)t - lane;
+			int rM = __shfl_up_sync(0xffffffffu, sM, 1);
+			int rL = __shfl_up_sync(0xffffffffu, sL, 1);
+			int rH = __shfl_up_sync(0xffffffffu, sH, 1);
+			int rC = __shfl_up_sync(0xffffffffu, sC, 1);
+			if (lane == 0) {
+				if (stripe == 0) {      // matrix row 0 at column t
+					if (MODE == MODE_GLOBAL)     { rM = NEGV; rL = NEGV; rH = 8 * (o + e * j) + m8; rC = ST_UPP; }          // :437-441
+					else if (MODE == MODE_LOCAL) { rM = ZERO + o8; rL = ZERO; rH = ZERO + m8; rC = ST_LOW; }
+					else                         { rM = ZERO + o8; rL = NEGV; rH = ZERO + m8; rC = ST_MID; }                // :619-624
+				} else {
+					const int4 b = sm.cring[t & 63u];
+					rM = b.x; rL = b.y; rH = b.z; rC = b.w;
+				}
+			}
+			if (checked && t == 0) { rH = pH; rC = pC; }      // step 0 only primes the pipeline: keep H(row0, 0)
+			int D = pH, DC = pC;
+			pH = rH; pC = rC;
+			if (!checked || (j >= 1 && j <= (int)l2)) {
+				const uint32_t y = (uint32_t)(j - 1) + sh;
+				const uint32_t c = (uint32_t)sm.rg.tring[y & 511u] << 16;
+				int jadd = 0;
+				if (JUMP) jadd = sm.rg.jring[y & 511u] ? AT_NEG : 8 * (a.jp - o);     // M[i][j-1] + jump, or barred (:659-665)
+				int Lup = rL, MoUp = rM, Mo = 0, Ln = 0, Hm = 0, code = 0;
+				const int kold = kbest;
+#pragma unroll
+				for (int r = 0; r < R; ++r) {
+					const int tt = (int)min(ac[r] ^ c, mu8);                      // 0 on a match, 8|m-u| otherwise
+					const int Mraw = tt * nsg + D;                                // H(i-1,j-1) + s
+					int Mn = Mraw, pm = DC;
+					if (MODE == MODE_LOCAL) { Mn = max(Mraw, ZERO); pm = DC | (int)min((uint32_t)(Mn - Mraw), 3u); }   // HOME (:825)
+					const int Lext = Lup + e8;
+					Ln = max(Lext, MoUp);
+					const int fL = (int)min((uint32_t)(Ln - Lext), 4u);           // gap opened only when strictly better (:456)
+					const int Un = __viaddmax_s32(Ul[r], e8, Mol[r]);
+					const int fU = (int)min((uint32_t)(Un - Mol[r]), 8u);         // gap extended only when strictly better (:460)
+					int Jn = 0, fJ = 0;
+					if (JUMP) {
+						const int ent = Mol[r] + jadd;
+						Jn = max(ent, Jl[r]);
+						fJ = (int)min((uint32_t)(Jn - ent), 1u);                  // stay in J only when strictly better (:660)
+					}
+					Mo = Mn + o8;
+					const int t1 = max(Ln, Mn);
+					int H = max(t1, Un);
+					code = (int)min((uint32_t)(H - Ln), 1u) + (int)min((uint32_t)(H - t1), 1u);   // first strictly greater, order L,M,U
+					if (JUMP) { const int H4 = max(H, Jn); code = max(code, (int)min((uint32_t)(H4 - H), 3u)); H = H4; }
+					Hm = H + m8;
+					acc[r] = acc[r] * 16u + (uint32_t)(pm | fL) + (uint32_t)fU;
+					if (JUMP) accJ[r] = accJ[r] * 2u + (uint32_t)fJ;
+					if (MODE == MODE_LOCAL) kbest = __viaddmax_s32(Mn, crow[r], kbest);
+					if (MODE == MODE_FIT) {
+						if (r == cap_r && j < (int)l2) {                         // column l2 excluded (:677, :684)
+							if (Mn > capM) { capM = Mn; capMj = j; }
+							if (Ln > capL) { capL = Ln; capLj = j; }
+						}
+					}
+					if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) { gH = H; gC = code; } }
+					D = Hl[r]; DC = Cl[r];
+					Hl[r] = Hm; Cl[r] = code; Ul[r] = Un; Mol[r] = Mo; if (JUMP) Jl[r] = Jn;
+					Lup = Ln; MoUp = Mo;
+				}
+				sM = Mo; sL = Ln; sH = Hm; sC = code;
+				if (MODE == MODE_LOCAL) { if (kbest != kold) tbest = (int)t; }
+				if (lane == 31 && !last_stripe) sm.stage[(uint32_t)j & 63u] = make_int4(sM, sL, sH, sC);
+			} else {
+#pragma unroll
+				for (int r = 0; r < R; ++r) { acc[r] *= 16u; if (JUMP) accJ[r] *= 2u; }
+			}
+		};
+
+		for (uint32_t tb = 0; tb <= t_last; tb += 8) {
+			if ((tb & 31u) == 0) {
+				__syncwarp();
+				if (!last_stripe && tb >= 64u) {      // lane 31 has finished the columns up to tb-32: flush (tb-64, tb-32]
+					const int cidx = (int)tb - 63 + lane;
+					if (cidx >= 1 && cidx <= (int)l2) __stcg(bnd_out + cidx, sm.stage[(uint32_t)cidx & 63u]);
+					__syncwarp();
+					if (lane == 0) st_release(a.prog + job, min(tb - 32u, l2));
+				}
+				if (stripe) {                         // block tb of the stripe above -> ring; fetch block tb+32
+					sm.cring[(tb + lane) & 63u] = pre;
+					const uint32_t nxt = tb + 32u + lane;
+					if (tb + 32u <= l2) {
+						wait_columns(prog_in, min(l2, tb + 63u), seen, lane);
+						if (nxt <= l2) pre = __ldcg(bnd_in + nxt);
+					}
+					__syncwarp();
+				}
+			}
+			if ((tb & 255u) == 32u && tb > 32u) {     // tile tb/256 - 1 is dead: refill its slot two tiles ahead
+				const uint32_t c = (tb >> 8) + 1u;
+				__syncwarp();
+				if (c < n_tiles) ring_issue<JUMP>(sm.rg, tbase16, jbase16, c, lane);
+			}
+			if ((tb & 255u) == 224u) {                // the first lane enters tile tb/256 + 1 within the next 32 steps
+				const uint32_t c = (tb >> 8) + 1u;
+				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
+			}
+			if (tb >= 32u && tb + 7u <= l2) {
+#pragma unroll
+				for (uint32_t k = 0; k < 8; ++k) step(tb + k, false);
+			} else {
+#pragma unroll
+				for (uint32_t k = 0; k < 8; ++k) step(tb + k, true);
+			}
+			if (want_ptr && (tb >> 3) < G) {
+				uint32_t *w = ptr + ((size_t)(stripe * G + (tb >> 3)) * 32 + lane) * R;
+#pragma unroll
+				for (int r = 0; r < R; ++r) w[r] = acc[r];
+			}
+			if (JUMP && want_ptr && (tb & 31u) == 24u && (tb >> 5) < GJ) {
+				uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (tb >> 5)) * 32 + lane) * R;
+#pragma unroll
+				for (int r = 0; r < R; ++r) w[r] = accJ[r];
+			}
+		}
+		__syncwarp();
+
+		if (!last_stripe) {       // rest of the boundary row: columns (t_last-63, t_last-31], and t_last-31 >= l2
+			const int cidx = (int)t_last - 62 + lane;
+			if (cidx >= 1 && cidx <= (int)l2) __stcg(bnd_out + cidx, sm.stage[(uint32_t)cidx & 63u]);
+			__syncwarp();
+			if (lane == 0) st_release(a.prog + job, l2);
+		}
+
+		// ---- end cell (reference: :466-469 global, :673-690 fit, running max :830-833 local) ----
+		if (MODE == MODE_LOCAL) {
+			int sc = -1, row = 0x7fffffff, col = 0;
+			if (kbest >= 0) { sc = kbest >> 3; row = (int)row0 + (7 - (kbest & 7)) + 1; col = tbest - lane; }
+#pragma unroll
+			for (int d = 16; d >= 1; d >>= 1) {
+				const int osc = __shfl_xor_sync(0xffffffffu, sc, d);
+				const int orow = __shfl_xor_sync(0xffffffffu, row, d);
+				const int ocol = __shfl_xor_sync(0xffffffffu, col, d);
+				if (osc > sc || (osc == sc && orow < row)) { sc = osc; row = orow; col = ocol; }
+			}
+			if (n_stripes > 1) {      // fold into the pair's chain: earlier stripes hold smaller rows and win ties
+				int32_t *ch = a.chain + 4 * (size_t)(p - a.pair_base);
+				if (stripe) {
+					wait_columns(prog_in, AT_PROG_DONE, seen, lane);
+					const int psc = __ldcg(ch + 0), prow = __ldcg(ch + 1), pcol = __ldcg(ch + 2);
+					if (psc >= sc) { sc = psc; row = prow; col = pcol; }
+				}
+				if (!last_stripe) {
+					if (lane == 0) { __stcg(ch + 0, sc); __stcg(ch + 1, row); __stcg(ch + 2, col); }
+					__syncwarp();
+					if (lane == 0) st_release(a.prog + job, AT_PROG_DONE);
+				}
+			}
+			if (last_stripe && lane == 0) { a.score[p] = sc; a.end_i[p] = row; a.end_j[p] = col; a.end_state[p] = ST_MID; }
+		} else if (last_stripe) {
+			const int owner = (int)(((l1 - 1) % RPP) / R);
+			if (lane == owner) {
+				if (MODE == MODE_GLOBAL) { a.score[p] = gH >> 3; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = (uint8_t)gC; }
+				else {
+					const bool useL = capL > capM;            // L replaces M only when strictly greater (:685)
+					a.score[p] = (useL ? capL : capM) >> 3; a.end_i[p] = l1; a.end_j[p] = useL ? capLj : capMj;
+					a.end_state[p] = useL ? ST_LOW : ST_MID;
+				}
+			}
+		}
+		__syncwarp();
+	}
+}
+
+// =====================================================================================
+// Single-plane kernel: overlap (max-plus, linear gap, 2-bit pointers) and edit distance
+// (min-plus, unit gaps, score only), int32 lanes, R = 1..8 rows per lane.
+//
+// Overlap keeps scores x4 and carries A = 4*M + 4*o (what the left and the upper neighbour
+// add anyway); the diagonal input is A + 4(m-o) minus the substitution penalty.  The 2-bit
+// pointer is two difference flags: bit 0 = diagonal beat left, bit 1 = up beat both
+// (reference order LEFT, DIAGONAL, RIGHT with first-strictly-greater ties, :944-947).
+// =====================================================================================
+template <int MODE, int R>
+__global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveArgs a)
+{
+	constexpr int RPP = 32 * R;
+	constexpr bool OV = MODE == MODE_OVERLAP;
+	struct __align__(16) Smem { WaveRing<false> rg; int cring[64]; int stage[64]; };
+	__shared__ Smem sm_all[AT_WAVE_WARPS];
+	Smem &sm = sm_all[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	if (lane == 0) { mbar_init(&sm.rg.bar[0], 1); mbar_init(&sm.rg.bar[1], 1); fence_proxy_async_smem(); }
+	__syncwarp();
+	uint32_t ring_par = 0;
+
+	// overlap: S = 4, step cost o, substitution m / u; edit: S = 1, step cost +1, substitution 0 / u
+	const int S = OV ? 4 : 1;
+	const int gap = OV ? S * a.o : 1;
+	const int dm = OV ? S * (a.m - a.o) : 0;                          // carried value -> diagonal input on a match
+	const uint32_t pen = OV ? (uint32_t)(S * (a.m >= a.u ? a.m - a.u : a.u - a.m)) : (uint32_t)(a.u >= 0 ? a.u : -a.u);
+	const int nsg = OV ? (a.m >= a.u ? -1 : 1) : (a.u >= 0 ? 1 : -1);
+	const bool want_ptr = OV && a.want_ptr != 0;
+
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0) job = atomicAdd(a.counter, 1u);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= a.n_tasks) break;
+		const WaveTask tk = a.tasks[job];
+		const uint32_t p = tk.pair, stripe = tk.stripe;
+		const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
+		const uint8_t *__restrict__ q = a.q + a.q_off[p];
+		const uint8_t *tbase = a.t + a.t_off[p];
+		const uint32_t sh = (uint32_t)((uintptr_t)tbase & 15u);
+		const uint8_t *tbase16 = tbase - sh;
+		const uint32_t n_tiles = (l2 + sh + 255u) >> 8;
+		uint32_t *__restrict__ ptr = OV ? a.ptr + a.ptr_off[p - a.pair_base] : nullptr;
+		const uint32_t G = (((l2 + 31u) | 15u) >> 4) + 1;                 // pointer-block geometry shared with K3
+		const uint32_t t_last = (l2 + 31u) | 31u;
+		const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
+		const bool last_stripe = stripe + 1 == n_stripes;
+		const uint32_t slab = (l2 + 4u) & ~3u;
+		int *bnd_pair = (int *)a.bnd + a.bnd_off[p - a.pair_base];
+		int *bnd_out = bnd_pair + (size_t)(stripe & 1u) * slab;
+		const int *bnd_in = bnd_pair + (size_t)((stripe & 1u) ^ 1u) * slab;
+		const uint32_t *prog_in = a.prog + (stripe ? job - 1 : job);
+		uint32_t seen = 0;
+		const uint32_t row0 = stripe * RPP + lane * R;
+
+		__syncwarp();
+		if (n_tiles > 0) ring_issue<false>(sm.rg, tbase16, nullptr, 0, lane);
+		if (n_tiles > 1) ring_issue<false>(sm.rg, tbase16, nullptr, 1, lane);
+
+		// carried value V: overlap 4*M + 4*o, edit M.  Column 0: M[i][0] = 0 (:938) | i (:301)
+		uint32_t ac[R], acc[R];
+		int Vl[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const uint32_t ri = row0 + r;
+			ac[r] = ri < l1 ? ((uint32_t)q[ri] << 16) : 0x4u;
+			Vl[r] = OV ? gap : (int)ri + 1;
+			acc[r] = 0;
+		}
+		int sV = Vl[R - 1];
+		int pD = 0;                                               // diagonal input of the lane's first row (set at the step with j = 0)
+		const int col0 = OV ? gap : (int)row0;                    // V(row0, 0): the row above this lane's strip
+		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
+		int capV = OV ? gap : 0, capJ = 0;                        // overlap: M[l1][0] = 0 seeds the search (:954-959)
+
+		int pre = 0;
+		if (stripe) {
+			wait_columns(prog_in, min(l2, 31u), seen, lane);
+			if ((uint32_t)lane <= l2) pre = __ldcg(bnd_in + lane);
+		}
+		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
+
+		auto step = [&](const uint32_t t, const bool checked) {
+			const int j = (int)t - lane;
+			int rV = __shfl_up_sync(0xffffffffu, sV, 1);
+			if (lane == 0) {
+				if (stripe == 0) rV = OV ? AT_NEGL : (int)t;                      // M[0][j] = -inf (:937) | j (:302)
+				else rV = sm.cring[t & 63u];
+				if (checked && t == 0) rV = col0;
+			}
+			int D = pD;
+			pD = rV + dm;
+			if (!checked || (j >= 1 && j <= (int)l2)) {
+				const uint32_t y = (uint32_t)(j - 1) + sh;
+				const uint32_t c = (uint32_t)sm.rg.tring[y & 511u] << 16;
+				int Vup = rV, v = 0;
+#pragma unroll
+				for (int r = 0; r < R; ++r) {
+					const int tt = (int)min(ac[r] ^ c, pen);                      // 0 on a match
+					const int diag = tt * nsg + D;
+					D = Vl[r] + dm;
+					if (OV) {
+						const int v1 = max(Vl[r], diag);                          // LEFT keeps ties (:944)
+						const int vm = max(v1, Vup);
+						const uint32_t f1 = min((uint32_t)(v1 - Vl[r]), 1u);      // DIAGONAL strictly greater
+						const uint32_t f2 = min((uint32_t)(vm - v1), 2u);         // RIGHT strictly greater
+						acc[r] = acc[r] * 4u + f1 + f2;
+						v = vm + gap;
+					} else {
+						v = __viaddmin_s32(min(Vl[r], Vup), 1, diag);             // min3 (:280-286)
+					}
+					Vl[r] = v; Vup = v;
+				}
+				sV = v;
+				if (lane == 31 && !last_stripe) sm.stage[(uint32_t)j & 63u] = sV;
+				if (cap_r >= 0) {                                                 // the pair's last row lives in this lane
+					int vc = Vl[0];
+#pragma unroll
+					for (int r = 1; r < R; ++r) if (cap_r == r) vc = Vl[r];
+					if (OV) { if (j < (int)l2 && vc > capV) { capV = vc; capJ = j; } }   // column l2 excluded (:955)
+					else if (j == (int)l2) capV = vc;
+				}
+			} else if (OV) {
+#pragma unroll
+				for (int r = 0; r < R; ++r) acc[r] *= 4u;
+			}
+		};
+
+		for (uint32_t tb = 0; tb <= t_last; tb += 16) {
+			if ((tb & 31u) == 0) {
+				__syncwarp();
+				if (!last_stripe && tb >= 64u) {
+					const int cidx = (int)tb - 63 + lane;
+					if (cidx >= 1 && cidx <= (int)l2) __stcg(bnd_out + cidx, sm.stage[(uint32_t)cidx & 63u]);
+					__syncwarp();
+					if (lane == 0) st_release(a.prog + job, min(tb - 32u, l2));
+				}
+				if (stripe) {
+					sm.cring[(tb + lane) & 63u] = pre;
+					const uint32_t nxt = tb + 32u + lane;
+					if (tb + 32u <= l2) {
+						wait_columns(prog_in, min(l2, tb + 63u), seen, lane);
+						if (nxt <= l2) pre = __ldcg(bnd_in + nxt);
+					}
+					__syncwarp();
+				}
+			}
+			if ((tb & 255u) == 32u && tb > 32u) {
+				const uint32_t c = (tb >> 8) + 1u;
+				__syncwarp();
+				if (c < n_tiles) ring_issue<false>(sm.rg, tbase16, nullptr, c, lane);
+			}
+			if ((tb & 255u) == 224u) {
+				const uint32_t c = (tb >> 8) + 1u;
+				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
+			}
+			if (tb >= 32u && tb + 15u <= l2) {
+#pragma unroll
+				for (uint32_t k = 0; k < 16; ++k) step(tb + k, false);
+			} else {
+#pragma unroll
+				for (uint32_t k = 0; k < 16; ++k) step(tb + k, true);
+			}
+			if (want_ptr && (tb >> 4) < G) {
+				uint32_t *w = ptr + ((size_t)(stripe * G + (tb >> 4)) * 32 + lane) * R;
+#pragma unroll
+				for (int r = 0; r < R; ++r) w[r] = acc[r];
+			}
+		}
+		__syncwarp();
+
+		if (!last_stripe) {
+			const int cidx = (int)t_last - 62 + lane;
+			if (cidx >= 1 && cidx <= (int)l2) __stcg(bnd_out + cidx, sm.stage[(uint32_t)cidx & 63u]);
+			__syncwarp();
+			if (lane == 0) st_release(a.prog + job, l2);
+		} else if (cap_r >= 0) {
+			if (OV) { a.score[p] = (capV - gap) / S; a.end_i[p] = l1; a.end_j[p] = capJ; a.end_state[p] = ST_MID; }
+			else { a.score[p] = capV; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = ST_MID; }
+		}
+		__syncwarp();
+	}
+}
+
+}  // namespace at
