@@ -9,6 +9,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaligntools_b200.so")
+ROOT = os.path.dirname(os.path.dirname(HERE))
+HOST_DIR = os.path.join(ROOT, "host")
+HOST_SOURCES = ["alignTools.c", "at_fasta.c"]
+HOST_HEADERS = ["at_fasta.h"]
+CLI = os.path.join(ROOT, "bin", "alignTools")
+FASTA_DUMP = os.path.join(ROOT, "bin", "at_fasta_dump")
 SOURCES = ["at_runtime.cu", "at_shim.cu"]
 HEADERS = ["at_kernels.cuh", "at_fill_affine.cuh", "at_wavefront.cuh", os.path.join("..", "..", "..", "include", "aligntools_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -23,7 +29,35 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _host_stale() -> bool:
+    if not os.path.exists(CLI) or not os.path.exists(FASTA_DUMP):
+        return True
+    t = min(os.path.getmtime(CLI), os.path.getmtime(FASTA_DUMP))
+    deps = [os.path.join(HOST_DIR, s) for s in HOST_SOURCES + HOST_HEADERS + ["at_fasta_dump.c"]] + [LIB, os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_host(force: bool = False) -> str:
+    """The C host (bin/alignTools): the reference's CLI over the C-ABI library, plus the FASTA
+    reader's test driver.  Plain gcc; the binary finds the library through an $ORIGIN rpath."""
+    if not force and not _host_stale():
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cflags = ["-std=gnu11", "-O2", "-g", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", HOST_DIR]
+    subprocess.run(["gcc"] + cflags + [os.path.join(HOST_DIR, s) for s in HOST_SOURCES] +
+                   ["-o", CLI, "-L", HERE, "-laligntools_b200", "-lz", "-Wl,-rpath,$ORIGIN/../aligntools/c_b200"], check=True)
+    subprocess.run(["gcc"] + cflags + [os.path.join(HOST_DIR, "at_fasta_dump.c"), os.path.join(HOST_DIR, "at_fasta.c")] +
+                   ["-o", FASTA_DUMP, "-lz"], check=True)
+    return CLI
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    lib = _build_lib(force, verbose)
+    build_host(force)
+    return lib
+
+
+def _build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     objs = []
@@ -39,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out.decode())
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = ["nvcc", "-shared", "-o", LIB] + objs + ["-lpthread"]
+    cmd = ["nvcc", "-arch=sm_100a", "-shared", "-o", LIB] + objs + ["-lpthread"]
     subprocess.run(cmd, check=True)
     return LIB
 

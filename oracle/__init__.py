@@ -215,3 +215,15 @@ def run_ref_cli(args, cwd=None):
     """Run the compiled reference CLI; returns (rc, stdout bytes, stderr bytes)."""
     pr = subprocess.run([REF_CLI] + list(args), capture_output=True, cwd=cwd)
     return pr.returncode, pr.stdout, pr.stderr
+
+
+def ref_kseq_dump(path: str) -> bytes | None:
+    """Records of a FASTA/FASTQ(.gz) file as the reference's kseq parser sees them (one line per
+    record: name, comment.s or "(null)", strlen(seq), seq); None when gzopen fails."""
+    lib = _load_ref()
+    lib.ref_kseq_dump.restype = C.c_long
+    lib.ref_kseq_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    cap = 8 * max(os.path.getsize(path), 1 << 12) + (1 << 16) if os.path.exists(path) else 1 << 12
+    buf = C.create_string_buffer(cap)
+    n = lib.ref_kseq_dump(path.encode(), buf, cap)
+    return None if n < 0 else buf.raw[:n]

@@ -119,3 +119,25 @@ int ref_align_batch(int mode, int m, int u, int o, int e, int j, int jump, size_
 	for (k = 0; k < n_threads; k++) { if (n_threads > 1) pthread_join(th[k], NULL); if (jobs[k].rc) rc = jobs[k].rc; }
 	return rc;
 }
+
+/* ---- the reference's FASTA path: kseq (src/kseq.h:189-229) exactly as kstring_read drives it
+ * (src/alignment.h:229-237), dumped one record per line as
+ *     <name>\t<comment.s or "(null)">\t<strlen(seq)>\t<seq>\n
+ * so tests can pin the host's own reader (host/at_fasta.c) on it.  Returns the number of bytes
+ * written (output truncated at cap), or -1 when the file cannot be opened. ---- */
+long ref_kseq_dump(const char *fname, char *out, size_t cap)
+{
+	gzFile fp = gzopen(fname, "r");
+	if (fp == NULL) return -1;
+	kseq_t *seq = kseq_init(fp);
+	size_t pos = 0;
+	while (kseq_read(seq) >= 0) {
+		int n = snprintf(out + pos, pos < cap ? cap - pos : 0, "%s\t%s\t%zu\t%s\n", seq->name.s,
+		                 seq->comment.s ? seq->comment.s : "(null)", strlen(seq->seq.s), seq->seq.s);
+		if (n < 0 || pos + (size_t)n >= cap) break;
+		pos += (size_t)n;
+	}
+	kseq_destroy(seq);
+	gzclose(fp);
+	return (long)pos;
+}
