@@ -307,6 +307,50 @@ class Aligner:
     def batch(self, mode, opt, q, q_off, q_len, t, t_off, t_len, **kw) -> Batch:
         return Batch(self, mode, opt, q, q_off, q_len, t, t_off, t_len, **kw)
 
+    def align_arrays(self, mode, opt, q, q_off, q_len, t, t_off, t_len, sites=None, site_off=None,
+                     out_flags=OUT_CIGAR, encoding=SEQ_BYTES, out: BatchResult = None,
+                     cigar_cap=None, aln_cap=None) -> BatchResult:
+        """One-shot at_batch_align (host arrays in, host arrays out; large batches are pipelined
+        H2D / kernels / D2H inside the library).  `out` may be a BatchResult from a previous call
+        whose buffers are reused; capacities default to the worst case (l1 + l2 per pair) for
+        the alignment strings and for the CIGARs (32 ops per pair once that exceeds 64 Mi ops;
+        AT_E_NOSPACE tells when to pass a larger cigar_cap)."""
+        md = _mode(mode)
+        n = int(len(q_len))
+        res = out if out is not None else BatchResult(n)
+        o = _Output()
+        o.score = res.score.ctypes.data
+        o.end_i, o.end_j = res.end_i.ctypes.data, res.end_j.ctypes.data
+        o.beg_i, o.beg_j = res.beg_i.ctypes.data, res.beg_j.ctypes.data
+        if out_flags & OUT_CIGAR and md != 4:
+            if cigar_cap is None:
+                worst = int(q_len.astype(np.uint64).sum() + t_len.astype(np.uint64).sum())     # one op per column
+                cigar_cap = worst if worst <= (1 << 26) else 32 * n + 1024
+            cap = int(cigar_cap)
+            if res.cigar is None or res.cigar.size < cap:
+                res.cigar = np.zeros(cap, np.uint32)
+                res.cigar_off = np.zeros(n + 1, np.uint64)
+            o.cigar, o.cigar_cap, o.cigar_off = res.cigar.ctypes.data, res.cigar.size, res.cigar_off.ctypes.data
+        if out_flags & OUT_ALN and md != 4:
+            cap = int(aln_cap if aln_cap is not None else int(q_len.astype(np.uint64).sum() + t_len.astype(np.uint64).sum()) + 16)
+            if res.aln1 is None or res.aln1.size < cap:
+                res.aln1 = np.zeros(cap, np.uint8)
+                res.aln2 = np.zeros(cap, np.uint8)
+                res.aln_off = np.zeros(n + 1, np.uint64)
+            o.aln1, o.aln2, o.aln_cap, o.aln_off = res.aln1.ctypes.data, res.aln2.ctypes.data, res.aln1.size, res.aln_off.ctypes.data
+        inp = _Input(n, encoding, q.ctypes.data, q_off.ctypes.data, q_len.ctypes.data,
+                     t.ctypes.data, t_off.ctypes.data, t_len.ctypes.data,
+                     sites.ctypes.data if sites is not None else None,
+                     site_off.ctypes.data if site_off is not None else None)
+        prm = opt.c()
+        tm = _Timing()
+        rc = self.lib.at_batch_align(self.h, md, C.byref(prm), C.byref(inp), out_flags, C.byref(o), C.byref(tm))
+        if rc:
+            raise AtError(rc, self.last_error())
+        res.timing = Timing(tm.fill_ms, tm.traceback_ms, tm.device_ms, tm.cells, tm.launches, tm.ptr_bytes,
+                            tm.fill_kernel_ms, tm.fill_kernel_cells)
+        return res
+
     def align(self, mode, reads, targets, opt: Opt = None, sites=None, out_flags=OUT_CIGAR | OUT_ALN) -> BatchResult:
         """Lists of bytes in, BatchResult out (create + run + fetch)."""
         opt = opt or Opt()

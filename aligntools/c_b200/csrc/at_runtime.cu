@@ -15,6 +15,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +33,7 @@ struct at_device {
 	int id = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // at_batch_align's pipeline streams (created on first use)
 };
 
 struct at_handle {
@@ -106,6 +109,7 @@ extern "C" void at_destroy(at_handle *h)
 	for (auto &d : h->devs) {
 		cudaSetDevice(d.id);
 		if (d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
+		for (auto &ps : d.pipe) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
 		cudaMemPool_t pool;
 		if (cudaDeviceGetDefaultMemPool(&pool, d.id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
 	}
@@ -167,7 +171,9 @@ struct Chunk {
 
 struct Shard {
 	at_device *dev = nullptr;
-	uint64_t p0 = 0, p1 = 0;            // global pair range
+	cudaStream_t stream = nullptr;      // the device's main stream, or a pipeline stream (at_batch_align)
+	uint64_t p0 = 0, p1 = 0;            // pair range within the batch's input arrays
+	uint64_t out_base = 0;              // index of pair p0 in the caller's output arrays
 	uint32_t n = 0;
 	DevBuf<uint8_t> d_q, d_t, d_jmask, d_rclass, d_end_state, d_q2, d_t2;
 	DevBuf<uint64_t> d_q_off, d_t_off, d_site_off;
@@ -226,7 +232,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
                        DevBuf<uint32_t> &d_len)
 {
 	const uint32_t n = s.n;
-	cudaStream_t st = s.dev->stream;
+	cudaStream_t st = s.stream;
 	std::vector<uint64_t> rel(n), unp(n);
 	uint64_t lo = UINT64_MAX, hi = 0, tot = 0;
 	bool monotonic = true;
@@ -274,9 +280,19 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 	return AT_OK;
 }
 
+// give the per-chunk buffers back to the pool (stream-ordered: the same stream reuses them at once)
+static void release_chunks(Shard &s)
+{
+	for (auto &c : s.chunks) {
+		c.d_ptr_off.release(); c.d_bnd_off.release(); for (auto &l : c.launches) { l.d_jobs.release(); l.d_tasks.release(); }
+		c.d_ops_off.release(); c.d_cols_off.release(); c.d_scratch_off.release(); c.d_cigar.release(); c.d_aln1.release(); c.d_aln2.release();
+	}
+	s.chunks.clear();
+}
+
 static void free_shard(Shard &s)
 {
-	if (s.dev) { cudaSetDevice(s.dev->id); tl_stream = s.dev->stream; }
+	if (s.dev) { cudaSetDevice(s.dev->id); tl_stream = s.stream; }
 	s.d_q.release(); s.d_t.release(); s.d_jmask.release(); s.d_rclass.release(); s.d_end_state.release();
 	s.d_q2.release(); s.d_t2.release();
 	s.d_q_off.release(); s.d_t_off.release(); s.d_site_off.release();
@@ -284,10 +300,7 @@ static void free_shard(Shard &s)
 	s.d_beg_j.release(); s.d_n_ops.release(); s.d_n_cols.release(); s.d_counter.release();
 	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_scratch.release(); s.d_bnd.release(); s.d_scan_tmp.release();
 	s.d_prog.release(); s.d_chain.release();
-	for (auto &c : s.chunks) {
-		c.d_ptr_off.release(); c.d_bnd_off.release(); for (auto &l : c.launches) { l.d_jobs.release(); l.d_tasks.release(); }
-		c.d_ops_off.release(); c.d_cols_off.release(); c.d_scratch_off.release(); c.d_cigar.release(); c.d_aln1.release(); c.d_aln2.release();
-	}
+	release_chunks(s);
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
 	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
 }
@@ -303,7 +316,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 {
 	at_handle *h = b->h;
 	CU(h, cudaSetDevice(s.dev->id));
-	cudaStream_t st = s.dev->stream;
+	cudaStream_t st = s.stream;
 	tl_stream = st;
 	const uint32_t n = s.n;
 	int rc;
@@ -364,7 +377,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	auto p16_ok = [&](uint32_t l1, uint32_t l2) {
 		return p16_mode && l1 <= 32u * MAXR && l2 <= 60000u && 8 * (int64_t)(l1 + l2 + 2) * maxabs < 32000;
 	};
-	s.chunks.clear();
+	release_chunks(s);      // a pipeline worker reuses its shard (and the shard-level buffers) for every sub-slice
 	uint64_t max_chunk_words = 0, max_scratch_words = 0;
 	{
 		Chunk cur; cur.k0 = 0;
@@ -505,22 +518,19 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		cudaError_t e = s.d_ptr.alloc(max_chunk_words);
 		if (e != cudaSuccess) { set_err(h, "pointer arena of %llu MB: %s", (unsigned long long)(max_chunk_words >> 18), cudaGetErrorString(e)); return AT_E_NOMEM; }
 	}
-	for (auto &e : s.ev) CU(h, cudaEventCreate(&e));
-	for (auto &e : s.evk) CU(h, cudaEventCreate(&e));
+	for (auto &e : s.ev) if (!e) CU(h, cudaEventCreate(&e));
+	for (auto &e : s.evk) if (!e) CU(h, cudaEventCreate(&e));
 	return AT_OK;
 }
 
-extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
-                               uint32_t out_flags, at_batch **out)
+// argument checks shared by at_batch_create and the pipelined at_batch_align; mirrors the reference's own failure modes
+static int validate_batch(at_handle *h, int mode, const at_params *p, const at_batch_input *in)
 {
-	if (!h || !p || !in || !out) return AT_E_ARG;
-	*out = nullptr;
 	if (mode < AT_GLOBAL || mode > AT_EDIT) { set_err(h, "bad mode %d", mode); return AT_E_ARG; }
 	if (!in->n_pairs || !in->q || !in->q_off || !in->q_len || !in->t || !in->t_off || !in->t_len) { set_err(h, "align: parameter error"); return AT_E_ARG; }
 	if (in->encoding != AT_SEQ_BYTES && in->encoding != AT_SEQ_2BIT) return AT_E_ARG;
 	if ((in->sites == nullptr) != (in->site_off == nullptr)) return AT_E_ARG;
 	if (in->n_pairs >= (1ull << 31)) return AT_E_ARG;
-	// validation mirrors the reference's own failure modes
 	int64_t maxabs = std::max<int64_t>({llabs((long long)p->m), llabs((long long)p->u), llabs((long long)p->o), llabs((long long)p->e), llabs((long long)p->j), 1});
 	for (uint64_t k = 0; k < in->n_pairs; ++k) {
 		const uint64_t l1 = in->q_len[k], l2 = in->t_len[k];
@@ -529,28 +539,50 @@ extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const
 		if (mode == AT_FIT && l2 < 2) { set_err(h, "pair %llu: fit with l2 < 2 is undefined in the reference", (unsigned long long)k); return AT_E_UNDEF; }
 		if ((int64_t)(l1 + l2 + 2) * maxabs >= (1ll << 27)) { set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
 	}
+	return AT_OK;
+}
+
+// contiguous slices of [lo, hi) with (nearly) equal numbers of cells; cut has parts + 1 entries
+static void cut_by_cells(const at_batch_input *in, uint64_t lo, uint64_t hi, size_t parts, std::vector<uint64_t> &cut)
+{
+	cut.assign(parts + 1, lo);
+	cut[parts] = hi;
+	if (parts <= 1) return;
+	uint64_t total = 0;                       // sum of l1*l2 <= 2^31 pairs x 2^54 would overflow; validate_batch bounds l1+l2 < 2^27
+	for (uint64_t k = lo; k < hi; ++k) total += (uint64_t)in->q_len[k] * in->t_len[k];
+	uint64_t acc = 0; size_t d = 1;
+	for (uint64_t k = lo; k < hi && d < parts; ++k) {
+		acc += (uint64_t)in->q_len[k] * in->t_len[k];
+		while (d < parts && (unsigned __int128)acc * parts >= (unsigned __int128)total * d) { cut[d++] = k + 1; }
+	}
+	for (; d < parts; ++d) cut[d] = hi;
+	cut[parts] = hi;
+}
+
+static at_batch *new_batch(at_handle *h, int mode, const at_params *p, uint32_t out_flags, uint64_t n)
+{
 	at_batch *b = new at_batch();
-	b->h = h; b->mode = mode; b->prm = *p; b->out_flags = out_flags; b->n = in->n_pairs;
+	b->h = h; b->mode = mode; b->prm = *p; b->out_flags = out_flags; b->n = n;
 	b->traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
+	return b;
+}
+
+extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
+                               uint32_t out_flags, at_batch **out)
+{
+	if (!h || !p || !in || !out) return AT_E_ARG;
+	*out = nullptr;
+	if (int rc = validate_batch(h, mode, p, in)) return rc;
+	at_batch *b = new_batch(h, mode, p, out_flags, in->n_pairs);
 	// contiguous slices balanced by cells
 	const size_t nd = h->devs.size();
-	std::vector<uint64_t> cut(nd + 1, 0);
-	{
-		long double total = 0;
-		for (uint64_t k = 0; k < b->n; ++k) total += (long double)in->q_len[k] * in->t_len[k];
-		long double acc = 0; size_t d = 1;
-		for (uint64_t k = 0; k < b->n && d < nd; ++k) {
-			acc += (long double)in->q_len[k] * in->t_len[k];
-			while (d < nd && acc >= total * d / nd) { cut[d++] = k + 1; }
-		}
-		for (; d < nd; ++d) cut[d] = b->n;
-		cut[nd] = b->n;
-	}
+	std::vector<uint64_t> cut;
+	cut_by_cells(in, 0, b->n, nd, cut);
 	b->shards.resize(nd);
 	std::vector<std::thread> th;
 	for (size_t d = 0; d < nd; ++d) {
 		Shard &s = b->shards[d];
-		s.dev = &h->devs[d]; s.p0 = cut[d]; s.p1 = cut[d + 1]; s.n = (uint32_t)(s.p1 - s.p0);
+		s.dev = &h->devs[d]; s.stream = s.dev->stream; s.p0 = cut[d]; s.p1 = cut[d + 1]; s.out_base = s.p0; s.n = (uint32_t)(s.p1 - s.p0);
 	}
 	auto work = [&](size_t d) { Shard &s = b->shards[d]; s.rc = s.n ? setup_shard(b, s, in) : AT_OK; };
 	if (nd == 1) work(0);
@@ -610,7 +642,7 @@ static int run_shard(at_batch *b, Shard &s)
 {
 	at_handle *h = b->h;
 	CU(h, cudaSetDevice(s.dev->id));
-	cudaStream_t st = s.dev->stream;
+	cudaStream_t st = s.stream;
 	tl_stream = st;
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
 	s.fill_ms = s.tb_ms = s.dev_ms = s.domk_ms = 0; s.domk_cells = 0; s.launches = 0;
@@ -754,6 +786,46 @@ extern "C" int at_batch_sizes(const at_batch *b, uint64_t *cigar_ops, uint64_t *
 	return AT_OK;
 }
 
+// D2H of one shard's results into the caller's arrays.  base_ops / base_cols: position of the
+// shard's first op / column in the dense outputs (advanced past this shard on return).  The
+// offset arrays receive entries [out_base, out_base + n) here; the final entry [n_total] is the
+// caller's job.
+static int fetch_shard(at_batch *b, Shard &s, at_batch_output *out, bool want_cig, bool want_aln,
+                       uint64_t &base_ops, uint64_t &base_cols)
+{
+	at_handle *h = b->h;
+	if (!s.n) return AT_OK;
+	CU(h, cudaSetDevice(s.dev->id));
+	cudaStream_t st = s.stream;
+	const uint64_t ob = s.out_base;
+	CU(h, cudaMemcpyAsync(out->score + ob, s.d_score.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	if (out->end_i) CU(h, cudaMemcpyAsync(out->end_i + ob, s.d_end_i.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	if (out->end_j) CU(h, cudaMemcpyAsync(out->end_j + ob, s.d_end_j.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	if (out->beg_i) CU(h, cudaMemcpyAsync(out->beg_i + ob, s.d_beg_i.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	if (out->beg_j) CU(h, cudaMemcpyAsync(out->beg_j + ob, s.d_beg_j.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	for (auto &c : s.chunks) {
+		const uint32_t nc = c.k1 - c.k0;
+		if (want_cig) {
+			CU(h, cudaMemcpyAsync(out->cigar_off + ob + c.k0, c.d_ops_off.p, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			if (c.tot_ops) CU(h, cudaMemcpyAsync(out->cigar + base_ops, c.d_cigar.p, c.tot_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		}
+		if (want_aln) {
+			CU(h, cudaMemcpyAsync(out->aln_off + ob + c.k0, c.d_cols_off.p, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			if (c.tot_cols) {
+				CU(h, cudaMemcpyAsync(out->aln1 + base_cols, c.d_aln1.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
+				CU(h, cudaMemcpyAsync(out->aln2 + base_cols, c.d_aln2.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
+			}
+		}
+		CU(h, cudaStreamSynchronize(st));
+		// chunk-local offsets -> global
+		if (want_cig && base_ops) for (uint32_t k = 0; k < nc; ++k) out->cigar_off[ob + c.k0 + k] += base_ops;
+		if (want_aln && base_cols) for (uint32_t k = 0; k < nc; ++k) out->aln_off[ob + c.k0 + k] += base_cols;
+		base_ops += c.tot_ops; base_cols += c.tot_cols;
+	}
+	CU(h, cudaStreamSynchronize(st));
+	return AT_OK;
+}
+
 extern "C" int at_batch_fetch(at_batch *b, at_batch_output *out)
 {
 	if (!b || !out || !b->ran || !out->score) return AT_E_ARG;
@@ -767,37 +839,10 @@ extern "C" int at_batch_fetch(at_batch *b, at_batch_output *out)
 	if (want_cig && tot_ops > out->cigar_cap) { set_err(h, "cigar buffer too small: need %llu ops", (unsigned long long)tot_ops); return AT_E_NOSPACE; }
 	if (want_aln && tot_cols > out->aln_cap) { set_err(h, "alignment buffer too small: need %llu bytes", (unsigned long long)tot_cols); return AT_E_NOSPACE; }
 	uint64_t base_ops = 0, base_cols = 0;
-	std::vector<uint64_t> tmp;
-	for (auto &s : b->shards) {
-		if (!s.n) continue;
-		CU(h, cudaSetDevice(s.dev->id));
-		cudaStream_t st = s.dev->stream;
-		CU(h, cudaMemcpyAsync(out->score + s.p0, s.d_score.p, s.n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-		if (out->end_i) CU(h, cudaMemcpyAsync(out->end_i + s.p0, s.d_end_i.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-		if (out->end_j) CU(h, cudaMemcpyAsync(out->end_j + s.p0, s.d_end_j.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-		if (out->beg_i) CU(h, cudaMemcpyAsync(out->beg_i + s.p0, s.d_beg_i.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-		if (out->beg_j) CU(h, cudaMemcpyAsync(out->beg_j + s.p0, s.d_beg_j.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-		for (auto &c : s.chunks) {
-			const uint32_t nc = c.k1 - c.k0;
-			if (want_cig) {
-				CU(h, cudaMemcpyAsync(out->cigar_off + s.p0 + c.k0, c.d_ops_off.p, (nc + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-				if (c.tot_ops) CU(h, cudaMemcpyAsync(out->cigar + base_ops, c.d_cigar.p, c.tot_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-			}
-			if (want_aln) {
-				CU(h, cudaMemcpyAsync(out->aln_off + s.p0 + c.k0, c.d_cols_off.p, (nc + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-				if (c.tot_cols) {
-					CU(h, cudaMemcpyAsync(out->aln1 + base_cols, c.d_aln1.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
-					CU(h, cudaMemcpyAsync(out->aln2 + base_cols, c.d_aln2.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
-				}
-			}
-			CU(h, cudaStreamSynchronize(st));
-			// chunk-local offsets -> global
-			if (want_cig && base_ops) for (uint32_t k = 0; k <= nc; ++k) out->cigar_off[s.p0 + c.k0 + k] += base_ops;
-			if (want_aln && base_cols) for (uint32_t k = 0; k <= nc; ++k) out->aln_off[s.p0 + c.k0 + k] += base_cols;
-			base_ops += c.tot_ops; base_cols += c.tot_cols;
-		}
-		CU(h, cudaStreamSynchronize(st));
-	}
+	for (auto &s : b->shards)
+		if (int rc = fetch_shard(b, s, out, want_cig, want_aln, base_ops, base_cols)) return rc;
+	if (want_cig) out->cigar_off[b->n] = base_ops;
+	if (want_aln) out->aln_off[b->n] = base_cols;
 	if (!b->traceback) {
 		if (out->cigar_off) for (uint64_t k = 0; k <= b->n; ++k) out->cigar_off[k] = 0;
 		if (out->aln_off) for (uint64_t k = 0; k <= b->n; ++k) out->aln_off[k] = 0;
@@ -805,9 +850,159 @@ extern "C" int at_batch_fetch(at_batch *b, at_batch_output *out)
 	return AT_OK;
 }
 
+// ------------------------------------------------------------- one-shot, pipelined ----
+// at_batch_align on a large batch: every device's slice is cut into sub-slices that go through
+// create (H2D) -> run (fill + traceback) -> fetch (D2H) on AT_PIPE_STREAMS streams, one host
+// thread per stream, so the copies of one sub-slice overlap the kernels of another.  Sub-slices
+// are claimed in pair order; a sub-slice's position in the dense CIGAR / alignment outputs is
+// known once every earlier sub-slice has finished its run (totals are published under a mutex).
+#define AT_PIPE_STREAMS 3
+static uint64_t env_u64(const char *name, uint64_t dflt) { const char *e = getenv(name); return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : dflt; }
+static uint64_t pipe_min_cells() { return env_u64("AT_PIPE_MIN_CELLS", 1ull << 31); }      // below this a batch is not worth cutting up
+static uint64_t pipe_slice_cells() { return env_u64("AT_PIPE_SLICE_CELLS", 1ull << 32); }  // target cells per sub-slice (2-3 ms of fill)
+
+struct PipeSlice { uint64_t lo = 0, hi = 0; size_t dev = 0; uint64_t tot_ops = 0, tot_cols = 0; bool known = false; };
+
+static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_batch_input *in, uint32_t out_flags,
+                           at_batch_output *out, at_timing *timing, uint64_t total_cells)
+{
+	const size_t nd = h->devs.size();
+	std::vector<uint64_t> dcut;
+	cut_by_cells(in, 0, in->n_pairs, nd, dcut);
+	std::vector<PipeSlice> slices;
+	std::vector<std::vector<size_t>> per_dev(nd);
+	for (size_t d = 0; d < nd; ++d) {
+		if (dcut[d + 1] == dcut[d]) continue;
+		uint64_t cells = 0;
+		for (uint64_t k = dcut[d]; k < dcut[d + 1]; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
+		size_t parts = (size_t)std::max<uint64_t>(1, cells / pipe_slice_cells());
+		parts = std::min<size_t>(parts, 64);
+		parts = std::min<size_t>(parts, (size_t)(dcut[d + 1] - dcut[d]));
+		std::vector<uint64_t> cut;
+		cut_by_cells(in, dcut[d], dcut[d + 1], parts, cut);
+		for (size_t k = 0; k < parts; ++k) {
+			if (cut[k + 1] == cut[k]) continue;
+			PipeSlice sl; sl.lo = cut[k]; sl.hi = cut[k + 1]; sl.dev = d;
+			per_dev[d].push_back(slices.size());
+			slices.push_back(sl);
+		}
+	}
+	// pipeline streams (created once per device)
+	for (size_t d = 0; d < nd; ++d) {
+		at_device &dv = h->devs[d];
+		if (!dv.pipe[0]) {
+			CU(h, cudaSetDevice(dv.id));
+			for (int w = 0; w < AT_PIPE_STREAMS; ++w) CU(h, cudaStreamCreateWithFlags(&dv.pipe[w], cudaStreamNonBlocking));
+		}
+	}
+	const bool traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
+	const bool want_cig = traceback && (out_flags & AT_OUT_CIGAR) && out->cigar;
+	const bool want_aln = traceback && (out_flags & AT_OUT_ALN) && out->aln1 && out->aln2;
+	if (want_cig && !out->cigar_off) return AT_E_ARG;
+	if (want_aln && !out->aln_off) return AT_E_ARG;
+
+	std::mutex mu; std::condition_variable cv;
+	std::atomic<int> failed{0};
+	// one sub-slice at a time owns a device's SMs: concurrent persistent fills would share them, finish
+	// together and leave the GPU idle while all workers prepare their next sub-slice in lockstep
+	std::vector<std::mutex> run_mu(nd);
+	std::vector<std::atomic<size_t>> next(nd);
+	for (auto &x : next) x = 0;
+	struct Acc { double fill = 0, tb = 0, dev = 0, domk = 0; uint64_t domc = 0, launches = 0, ptr = 0; };
+	std::vector<Acc> acc(nd * AT_PIPE_STREAMS);
+
+	const bool trace = getenv("AT_PIPE_TRACE") != nullptr;      // host timeline of every sub-slice on stderr
+	const auto t_origin = std::chrono::steady_clock::now();
+	auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(); };
+	auto worker = [&](size_t d, int w) {
+		at_device &dv = h->devs[d];
+		Acc &a = acc[d * AT_PIPE_STREAMS + w];
+		// one workspace per worker: the sequence buffers, pointer arena and scratch of the first
+		// sub-slice are reused by the later ones (no allocator traffic inside the pipeline)
+		at_batch *b = new_batch(h, mode, p, out_flags, 0);
+		b->shards.resize(1);
+		for (;;) {
+			const size_t k = next[d].fetch_add(1);
+			if (k >= per_dev[d].size() || failed.load()) break;
+			const size_t si = per_dev[d][k];
+			PipeSlice &sl = slices[si];
+			at_batch_input sub = *in;
+			sub.n_pairs = sl.hi - sl.lo;
+			sub.q_off = in->q_off + sl.lo; sub.q_len = in->q_len + sl.lo;
+			sub.t_off = in->t_off + sl.lo; sub.t_len = in->t_len + sl.lo;
+			if (in->site_off) sub.site_off = in->site_off + sl.lo;
+			b->n = sub.n_pairs;
+			Shard &s = b->shards[0];
+			s.dev = &dv; s.stream = dv.pipe[w]; s.p0 = 0; s.p1 = sub.n_pairs; s.n = (uint32_t)sub.n_pairs; s.out_base = sl.lo;
+			const double t_a = now_ms();
+			int rc = setup_shard(b, s, &sub);
+			const double t_b = now_ms();
+			if (!rc) { std::lock_guard<std::mutex> own(run_mu[d]); rc = run_shard(b, s); }
+			const double t_c = now_ms();
+			uint64_t to = 0, tc = 0;
+			if (!rc) for (auto &c : s.chunks) { to += c.tot_ops; tc += c.tot_cols; }
+			uint64_t base_ops = 0, base_cols = 0;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				sl.tot_ops = to; sl.tot_cols = tc; sl.known = true;
+				if (rc) failed = rc;
+				cv.notify_all();
+				cv.wait(lk, [&] { if (failed.load()) return true; for (size_t x = 0; x < si; ++x) if (!slices[x].known) return false; return true; });
+				for (size_t x = 0; x < si; ++x) { base_ops += slices[x].tot_ops; base_cols += slices[x].tot_cols; }
+			}
+			if (!rc && !failed.load()) {
+				if ((want_cig && base_ops + to > out->cigar_cap) || (want_aln && base_cols + tc > out->aln_cap)) {
+					set_err(h, "output buffer too small: need at least %llu ops / %llu bytes", (unsigned long long)(base_ops + to), (unsigned long long)(base_cols + tc));
+					rc = AT_E_NOSPACE;
+				} else rc = fetch_shard(b, s, out, want_cig, want_aln, base_ops, base_cols);
+			}
+			if (trace) fprintf(stderr, "[at pipe] dev %zu stream %d slice %zu pairs %llu: setup %.2f-%.2f run -%.2f fetch -%.2f ms (fill %.2f tb %.2f)\n",
+			                   d, w, si, (unsigned long long)sub.n_pairs, t_a, t_b, t_c, now_ms(), s.fill_ms, s.tb_ms);
+			a.fill += s.fill_ms; a.tb += s.tb_ms; a.dev += s.dev_ms; a.launches += s.launches; a.ptr += traceback ? s.ptr_bytes : 0;
+			if (s.domk_cells > a.domc) { a.domc = s.domk_cells; a.domk = s.domk_ms; }
+			if (rc) { std::lock_guard<std::mutex> lk(mu); failed = rc; cv.notify_all(); break; }
+		}
+		if (b->shards[0].dev) at_batch_free(b); else delete b;
+	};
+	std::vector<std::thread> th;
+	for (size_t d = 0; d < nd; ++d)
+		for (int w = 0; w < AT_PIPE_STREAMS; ++w) th.emplace_back(worker, d, w);
+	for (auto &t : th) t.join();
+	if (failed.load()) return failed.load();
+	uint64_t all_ops = 0, all_cols = 0;
+	for (auto &sl : slices) { all_ops += sl.tot_ops; all_cols += sl.tot_cols; }
+	if (want_cig) out->cigar_off[in->n_pairs] = all_ops;
+	if (want_aln) out->aln_off[in->n_pairs] = all_cols;
+	if (!traceback) {
+		if (out->cigar_off) for (uint64_t k = 0; k <= in->n_pairs; ++k) out->cigar_off[k] = 0;
+		if (out->aln_off) for (uint64_t k = 0; k <= in->n_pairs; ++k) out->aln_off[k] = 0;
+	}
+	if (timing) {
+		memset(timing, 0, sizeof *timing);
+		timing->cells = total_cells;
+		for (size_t d = 0; d < nd; ++d) {
+			double fill = 0, tb = 0, dev = 0;
+			for (int w = 0; w < AT_PIPE_STREAMS; ++w) {
+				const Acc &a = acc[d * AT_PIPE_STREAMS + w];
+				fill += a.fill; tb += a.tb; dev += a.dev; timing->launches += a.launches; timing->ptr_bytes += a.ptr;
+				if (a.domc > timing->fill_kernel_cells) { timing->fill_kernel_cells = a.domc; timing->fill_kernel_ms = a.domk; }
+			}
+			timing->fill_ms = std::max(timing->fill_ms, fill); timing->traceback_ms = std::max(timing->traceback_ms, tb);
+			timing->device_ms = std::max(timing->device_ms, dev);     // sum of the sub-slices' device times (they overlap)
+		}
+	}
+	return AT_OK;
+}
+
 extern "C" int at_batch_align(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
                               uint32_t out_flags, at_batch_output *out, at_timing *timing)
 {
+	if (!h || !p || !in || !out || !out->score) return AT_E_ARG;
+	if (int rc = validate_batch(h, mode, p, in)) return rc;
+	uint64_t cells = 0;
+	for (uint64_t k = 0; k < in->n_pairs; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
+	if (cells >= pipe_min_cells() && in->n_pairs >= 16 && !getenv("AT_NO_PIPELINE"))
+		return align_pipelined(h, mode, p, in, out_flags, out, timing, cells);
 	at_batch *b = nullptr;
 	int rc = at_batch_create(h, mode, p, in, out_flags, &b);
 	if (rc) return rc;

@@ -218,3 +218,45 @@ def test_reference_named_operators(A):
     assert (sc, r1, r2) == (0.0, b"", b"")                             # golden B16
     with pytest.raises(ValueError):
         A.align_fit_affine_jump(b"PLEASANTLY", b"MEANLY")
+
+
+@pytest.mark.parametrize("mode", ["local", "fitjump", "overlap", "edit"])
+def test_pipelined_one_shot_equals_three_call_path(A, aligner, monkeypatch, mode):
+    """at_batch_align cuts a large batch into sub-slices that overlap H2D / kernels / D2H on
+    several streams; results (scores, cells, dense CIGAR + alignment strings and their offsets)
+    must be identical to create + run + fetch on the whole batch."""
+    rng = random.Random(77)
+    q, t = _random_batch(rng, 600, (20, 500), (0, 150), fit=mode.startswith("fit"))
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    prm = dict(m=2, u=-3, o=-4, e=-1, j=-7, jump=(mode == "fitjump"))
+    sites = site_off = None
+    if mode == "fitjump":
+        ss, so = [], [0]
+        for s2 in t:
+            ss += sorted(rng.randrange(len(s2)) for _ in range(rng.choice([0, 2, 5]))); so.append(len(ss))
+        sites = np.array(ss + [0], dtype=np.int32); site_off = np.array(so, dtype=np.uint64)
+    md = "fit" if mode == "fitjump" else mode
+    opt = A.Opt(**prm)
+    flags = 0 if md == "edit" else 3
+    b = aligner.batch(md, opt, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off, out_flags=flags)
+    b.run()
+    ref = b.fetch()
+    b.free()
+    monkeypatch.setenv("AT_PIPE_MIN_CELLS", "1")
+    monkeypatch.setenv("AT_PIPE_SLICE_CELLS", "3000000")        # about 10 sub-slices
+    res = aligner.align_arrays(md, opt, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off, out_flags=flags)
+    assert res.timing.launches > ref.n // 100
+    assert np.array_equal(res.score, ref.score)
+    if md != "edit":
+        for name in ("end_i", "end_j", "beg_i", "beg_j", "cigar_off", "aln_off"):
+            assert np.array_equal(getattr(res, name), getattr(ref, name)), name
+        no, nc = int(ref.cigar_off[-1]), int(ref.aln_off[-1])
+        assert np.array_equal(res.cigar[:no], ref.cigar[:no])
+        assert np.array_equal(res.aln1[:nc], ref.aln1[:nc]) and np.array_equal(res.aln2[:nc], ref.aln2[:nc])
+    # too small an output buffer is an error, not a silent truncation
+    if md != "edit":
+        with pytest.raises(A.AtError) as e:
+            aligner.align_arrays(md, opt, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off,
+                                 out_flags=1, cigar_cap=16)
+        assert e.value.rc == -5
