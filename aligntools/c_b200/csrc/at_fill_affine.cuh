@@ -20,8 +20,13 @@
 //   * packed lanes are BIASED by 0x8000 per half and compared unsigned, so every add/subtract is
 //     an ordinary 32-bit integer instruction (no carry can cross the halves while the values
 //     stay in range, which the host checks) and can be issued on the FMA pipe;
-//   * symbols are pre-shifted (<<8 / <<16), so  min(a ^ b, 8|m-u|)  is 0 on a match and the
-//     whole substitution penalty otherwise;  M = (H+m) - that;
+//   * PROF variant (target alphabet of the shard has at most 4 distinct bytes -- DNA): a per-warp QUERY
+//     PROFILE in shared memory, rebuilt per job: word[comb][lane][r] = 8*s(read row, target symbol) for
+//     pair A (+ the same for pair B << 16, comb = codeA*4 + codeB), so  M = H(i-1,j-1) + word  is one
+//     LDS (64-bit, two rows at a time) and one add; the target ring holds the byte offset of `comb`;
+//   * fallback variant (any byte alphabet): symbols are pre-shifted (<<8 / <<16), so
+//     min(a ^ b, 8|m-u|)  is 0 on a match and the whole substitution penalty otherwise;
+//     M = (H+m) - that;
 //   * local mode keeps the lane's running maximum of  8*M + (7 - row_in_lane)  with one
 //     VIADDMNMX per cell: larger score first, then the smaller row -- together with "first step
 //     at which the key reached its final value" this is the reference's first maximum in
@@ -36,6 +41,16 @@ namespace at {
 
 #define AT_RING 512        // target ring entries per warp (two 256-column blocks)
 #define AT_FILL_WARPS 4
+
+// query-profile geometry: words per lane (>= R, even, half of it odd: conflict-free 64-bit loads)
+__host__ __device__ constexpr int prof_lane_stride(int R) { return R <= 2 ? 2 : (R <= 6 ? 6 : 10); }
+__host__ __device__ constexpr int prof_combs(bool packed) { return packed ? 16 : 4; }
+// dynamic shared memory of one CTA of at_fill_affine<.., R, .., PACKED, PROF>
+__host__ __device__ constexpr size_t fill_smem_bytes(int R, bool packed, bool prof)
+{
+	return (size_t)AT_FILL_WARPS * (prof ? (size_t)AT_RING * 2 + (size_t)prof_combs(packed) * 32 * prof_lane_stride(R) * 4
+	                                     : (size_t)AT_RING * 4);
+}
 
 template <bool PACKED> struct Lanes;
 
@@ -71,6 +86,8 @@ struct FillArgs2 {
 	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
 	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
 	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
+	const uint8_t  *symmap;  // PROF: byte -> code 0..3 of the shard's target alphabet (256 entries)
+	uint32_t        syms;    // PROF: the byte of code c in bits 8c..8c+7
 	const FillJob  *jobs;
 	uint32_t        n_jobs;
 	uint32_t       *counter;
@@ -80,7 +97,7 @@ struct FillArgs2 {
 	int             want_ptr;
 };
 
-template <int MODE, int R, bool JUMP, bool PACKED>
+template <int MODE, int R, bool JUMP, bool PACKED, bool PROF>
 __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillArgs2 a)
 {
 	typedef Lanes<PACKED> V;
@@ -88,13 +105,23 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 	static_assert(!PACKED || (MODE == MODE_LOCAL && !JUMP), "packed lanes: local mode");
 	constexpr uint32_t SPW = V::STEPS_PER_WORD;
 	constexpr int RPP = 32 * R;
+	constexpr int LS = prof_lane_stride(R), NC = prof_combs(PACKED);
+	constexpr uint32_t COMB_BYTES = 32u * LS * 4u;             // one comb's slice of the profile
+	constexpr size_t WARP_BYTES = fill_smem_bytes(R, PACKED, PROF) / AT_FILL_WARPS;
 
-	__shared__ uint32_t ring_all[AT_FILL_WARPS][AT_RING];
+	extern __shared__ __align__(16) unsigned char fill_smem[];
 	const int lane = threadIdx.x & 31;
-	uint32_t *ring = ring_all[threadIdx.x >> 5];
+	unsigned char *warp_smem = fill_smem + (threadIdx.x >> 5) * WARP_BYTES;
+	uint32_t *ring = (uint32_t *)warp_smem;                                   // !PROF: one u32 per column
+	uint16_t *ring16 = (uint16_t *)warp_smem;                                 // PROF: byte offset of the column's comb (| blacklist bit)
+	uint32_t *prof = (uint32_t *)(warp_smem + AT_RING * 2);                   // PROF: [NC][32][LS]
+	const unsigned char *prof_lane = (const unsigned char *)(prof + lane * LS);
 
 	const int m = a.m, u = a.u, o = a.o, e = a.e;
 	const T m8 = V::delta(m), o8 = V::delta(o), e8 = V::delta(e), e8h = V::delta_h(e);
+	const T HM = PROF ? (T)0 : m8;                                            // the carried H holds H + m in the fallback variant
+	T nz = lane ? 1 : 0;                                                      // lane 0 takes matrix row 0 instead of a neighbour
+	asm volatile("" : "+r"(nz));                                              // opaque: keep x * nz + b0 a multiply-add (FMA pipe), not a SEL
 	const uint32_t mu8 = (uint32_t)(8 * (m >= u ? m - u : u - m));     // per half; < 1 << CSHIFT (host-checked)
 	const int nsg = m >= u ? -1 : 1;                                    // M = (H+m) - penalty  (or + when u > m)
 	const T ZERO = V::value(0);
@@ -118,18 +145,30 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 		constexpr uint32_t n_stripes = 1;
 		uint32_t *__restrict__ ptrJ = ptr + (size_t)n_stripes * G * RPP;
 
-		// ring[(j-1) & 511]: packed (tA << 8) | (tB << 24); int32 (tA << 16) | blacklist bit
+		// ring[(j-1) & 511]: packed (tA << 8) | (tB << 24); int32 (tA << 16) | blacklist bit;
+		// PROF: byte offset of the column's comb in the profile | blacklist bit
 		auto load_block = [&](uint32_t blk) {
 			const uint32_t base = blk * 256u;
 #pragma unroll
 			for (int k = 0; k < 8; ++k) {
 				const uint32_t idx = base + k * 32u + lane;
-				uint32_t v = PACKED ? 0x00010001u : 0x2u;      // past the end: never equals a symbol
-				if (idx < l2) {
-					if (PACKED) v = ((uint32_t)__ldg(tA + idx) << 8) | ((uint32_t)__ldg(tB + idx) << 24);
-					else { v = (uint32_t)__ldg(tA + idx) << 16; if (JUMP) v |= __ldg(jm + idx) ? 1u : 0u; }
+				if (PROF) {
+					uint32_t v = 0;                            // past the end: any comb (those cells are never read back)
+					if (idx < l2) {
+						v = __ldg(a.symmap + __ldg(tA + idx));
+						if (PACKED) v = v * 4u + __ldg(a.symmap + __ldg(tB + idx));
+						v *= COMB_BYTES;
+						if (JUMP) v |= __ldg(jm + idx) ? 1u : 0u;
+					}
+					ring16[idx & (AT_RING - 1)] = (uint16_t)v;
+				} else {
+					uint32_t v = PACKED ? 0x00010001u : 0x2u;      // past the end: never equals a symbol
+					if (idx < l2) {
+						if (PACKED) v = ((uint32_t)__ldg(tA + idx) << 8) | ((uint32_t)__ldg(tB + idx) << 24);
+						else { v = (uint32_t)__ldg(tA + idx) << 16; if (JUMP) v |= __ldg(jm + idx) ? 1u : 0u; }
+					}
+					ring[idx & (AT_RING - 1)] = v;
 				}
-				ring[idx & (AT_RING - 1)] = v;
 			}
 		};
 
@@ -163,51 +202,80 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					crow[r] = (T)(ri < l1A ? 7 - r : -(1 << 28));
 				}
 				// column 0 (left border)
-				if (MODE == MODE_GLOBAL)     { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = V::value(o + e * i) + m8; Cl[r] = V::raw(ST_LOW); }   // :432-436
-				else if (MODE == MODE_LOCAL) { Mol[r] = ZERO + o8; Ul[r] = ZERO; Hl[r] = ZERO + m8; Cl[r] = V::raw(ST_LOW); }             // calloc zeros
+				if (MODE == MODE_GLOBAL)     { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = V::value(o + e * i) + HM; Cl[r] = V::raw(ST_LOW); }   // :432-436
+				else if (MODE == MODE_LOCAL) { Mol[r] = ZERO + o8; Ul[r] = ZERO; Hl[r] = ZERO + HM; Cl[r] = V::raw(ST_LOW); }             // calloc zeros
 				else                         { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = NEGV; Cl[r] = V::raw(ST_MID); }                       // :612-617
 				Jl[r] = NEGV; acc[r] = 0; accJ[r] = 0;
+				if (PROF) {     // this lane's rows of the query profile: 8*s(read symbol, target symbol of code c)
+					const uint32_t qa = ri < l1A ? (uint32_t)qA[ri] : 0x100u, qb = (PACKED && ri < l1B) ? (uint32_t)qB[ri] : 0x100u;
+					int sa[4], sb[4];
+#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						const uint32_t sy = (a.syms >> (8 * c)) & 255u;
+						sa[c] = 8 * (qa == sy ? m : u); sb[c] = 8 * (qb == sy ? m : u);
+					}
+#pragma unroll
+					for (int c = 0; c < NC; ++c)
+						prof[(c * 32 + lane) * LS + r] = PACKED ? (uint32_t)(sa[c >> 2] + sb[c & 3] * 65536) : (uint32_t)sa[c];
+				}
 			}
+			if (PROF) __syncwarp();
 			T sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
 			T sL = MODE == MODE_GLOBAL ? V::value(o + e * (int)(row0 + R)) : (MODE == MODE_LOCAL ? ZERO : NEGV);
 			T pH, pC;      // H(row0, 0) + m and its code
 			if (row0 == 0) {
-				if (MODE == MODE_GLOBAL)     { pH = V::value(o < 0 ? 0 : o) + m8; pC = V::raw(o < 0 ? ST_MID : ST_LOW); }   // max5(L=o, M=0, U=o)
-				else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = V::raw(ST_LOW); }
-				else                         { pH = ZERO + m8; pC = V::raw(ST_MID); }                                       // M[0][0]=U[0][0]=0
+				if (MODE == MODE_GLOBAL)     { pH = V::value(o < 0 ? 0 : o) + HM; pC = V::raw(o < 0 ? ST_MID : ST_LOW); }   // max5(L=o, M=0, U=o)
+				else if (MODE == MODE_LOCAL) { pH = ZERO + HM; pC = V::raw(ST_LOW); }
+				else                         { pH = ZERO + HM; pC = V::raw(ST_MID); }                                       // M[0][0]=U[0][0]=0
 			} else {
-				if (MODE == MODE_GLOBAL)     { pH = V::value(o + e * (int)row0) + m8; pC = V::raw(ST_LOW); }
-				else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = V::raw(ST_LOW); }
+				if (MODE == MODE_GLOBAL)     { pH = V::value(o + e * (int)row0) + HM; pC = V::raw(ST_LOW); }
+				else if (MODE == MODE_LOCAL) { pH = ZERO + HM; pC = V::raw(ST_LOW); }
 				else                         { pH = NEGV; pC = V::raw(ST_MID); }
 			}
+			// matrix row 0 as lane 0 sees it (zero in every other lane: x = neighbour * nz + b0)
+			T b0M, b0L, b0H, b0C, b0E = 0;
+			if (MODE == MODE_GLOBAL)     { b0M = NEGV; b0L = NEGV; b0H = V::value(o) + HM; b0C = V::raw(ST_UPP); b0E = e8; }         // :437-441, U[0][j] = o + e j
+			else if (MODE == MODE_LOCAL) { b0M = ZERO + o8; b0L = ZERO; b0H = ZERO + HM; b0C = V::raw(ST_LOW); }
+			else                         { b0M = ZERO + o8; b0L = NEGV; b0H = ZERO + HM; b0C = V::raw(ST_MID); }                     // :619-624
+			if (lane) { b0M = 0; b0L = 0; b0H = 0; b0C = 0; b0E = 0; }
 			const int cap_r = (!PACKED && last_stripe && lane == (int)(((l1A - 1) % RPP) / R)) ? (int)((l1A - 1) % R) : -1;
 			T kbest = PACKED ? (T)0 : (T)AT_NEG_INIT;     // below every real key
 			T tbest = 0;
 
-			auto step = [&](const uint32_t t, const bool checked) {
+			// first step at which the running key took its (so far) final value -> column of the running maximum
+			auto note_best = [&](const T before, const T after, const uint32_t t) {
+				if (PACKED) { const T chg = V::flag(after ^ before, 1) * 0xffffu; tbest = (tbest & ~chg) | ((T)(t * 0x10001u) & chg); }
+				else if (after != before) tbest = (T)t;
+			};
+			// `first`: first step of a pointer word -- the accumulator restarts instead of shifting
+			auto step = [&](const uint32_t t, const bool checked, const bool first) {
 				const int j = (int)t - lane;
-				T rM = __shfl_up_sync(0xffffffffu, sM, 1);
-				T rL = __shfl_up_sync(0xffffffffu, sL, 1);
-				T rH = __shfl_up_sync(0xffffffffu, sH, 1);
-				T rC = __shfl_up_sync(0xffffffffu, sC, 1);
-				if (lane == 0) {     // matrix row 0 at column j = t
-					if (MODE == MODE_GLOBAL)     { rM = NEGV; rL = NEGV; rH = V::value(o + e * j) + m8; rC = V::raw(ST_UPP); }   // :437-441
-					else if (MODE == MODE_LOCAL) { rM = ZERO + o8; rL = ZERO; rH = ZERO + m8; rC = V::raw(ST_LOW); }
-					else                         { rM = ZERO + o8; rL = NEGV; rH = ZERO + m8; rC = V::raw(ST_MID); }             // :619-624
-				}
+				// neighbour's last row, or matrix row 0 at column j = t in lane 0 (multiply-add: keeps the ALU pipe free)
+				T rM = __shfl_up_sync(0xffffffffu, sM, 1) * nz + b0M;
+				T rL = __shfl_up_sync(0xffffffffu, sL, 1) * nz + b0L;
+				T rH = __shfl_up_sync(0xffffffffu, sH, 1) * nz + b0H;
+				T rC = __shfl_up_sync(0xffffffffu, sC, 1) * nz + b0C;
+				if (MODE == MODE_GLOBAL) rH += b0E * (T)t;
 				if (checked && t == 0) { rH = pH; rC = pC; }   // step 0 only primes the pipeline: keep H(row0, 0)
 				T D = pH, DC = pC;
 				pH = rH; pC = rC;
 				if (!checked || (j >= 1 && j <= (int)l2)) {
-					uint32_t c = ring[(uint32_t)(j - 1) & (AT_RING - 1)];
+					uint32_t c = PROF ? (uint32_t)ring16[(uint32_t)(j - 1) & (AT_RING - 1)] : ring[(uint32_t)(j - 1) & (AT_RING - 1)];
 					T jadd = 0;
 					if (JUMP) { jadd = (c & 1u) ? (T)AT_NEG : V::delta(a.jp - o); c &= ~1u; }   // M[i][j-1] + jump, or barred (:659-665)
+					uint32_t pw[LS];                                // PROF: the profile words of this lane's rows for the column's comb
+					if (PROF) {
+						const uint2 *pp = (const uint2 *)(prof_lane + c);
+#pragma unroll
+						for (int r2 = 0; r2 < (R + 1) / 2; ++r2) { const uint2 v2 = pp[r2]; pw[2 * r2] = v2.x; pw[2 * r2 + 1] = v2.y; }
+					}
 					T Lup = rL, MoUp = rM, Mo = 0, Ln = 0, Hm = 0, code = 0;
 					const T kold = kbest;
 #pragma unroll
 					for (int r = 0; r < R; ++r) {
-						const T tt = V::flag((T)(ac[r] ^ c), mu8);              // 0 on a match, 8|m-u| otherwise
-						const T Mraw = tt * (T)nsg + D;                         // H(i-1,j-1) + s
+						T Mraw;                                                 // H(i-1,j-1) + s
+						if (PROF) Mraw = D + (T)pw[r];
+						else { const T tt = V::flag((T)(ac[r] ^ c), mu8); Mraw = tt * (T)nsg + D; }   // tt: 0 on a match, 8|m-u| otherwise
 						T Mn = Mraw, pm = DC;
 						if (MODE == MODE_LOCAL) { Mn = V::vmax(Mraw, ZERO); pm = DC | V::flag(Mn - Mraw, 3); }   // HOME: 0.0 strictly greater (:825)
 						const T Lext = Lup + e8;
@@ -226,8 +294,8 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 						T H = V::vmax(t1, Un);
 						code = V::flag(H - Ln, 1) + V::flag(H - t1, 1);         // 0 LOW, 1 MID, 2 UPP: first strictly greater, order L,M,U
 						if (JUMP) { const T H4 = V::vmax(H, Jn); code = V::vmax(code, V::flag(H4 - H, 3)); H = H4; }
-						Hm = H + m8;
-						acc[r] = acc[r] * 16u + (uint32_t)(pm | fL) + (uint32_t)fU;
+						Hm = H + HM;
+						acc[r] = (first ? 0u : acc[r] * 16u) + (uint32_t)(pm | fL) + (uint32_t)fU;
 						if (JUMP) accJ[r] = accJ[r] * 2u + (uint32_t)fJ;
 						if (MODE == MODE_LOCAL) kbest = V::addmax(Mn, crow[r], kbest);
 						if (MODE == MODE_FIT) {
@@ -242,13 +310,10 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 						Lup = Ln; MoUp = Mo;
 					}
 					sM = Mo; sL = Ln; sH = Hm; sC = code;
-					if (MODE == MODE_LOCAL) {     // first step at which the running key took its (so far) final value
-						if (PACKED) { const T chg = V::flag(kbest ^ kold, 1) * 0xffffu; tbest = (tbest & ~chg) | ((T)(t * 0x10001u) & chg); }
-						else if (kbest != kold) tbest = (T)t;
-					}
+					if (MODE == MODE_LOCAL) note_best(kold, kbest, t);
 				} else {
 #pragma unroll
-					for (int r = 0; r < R; ++r) { acc[r] *= 16u; if (JUMP) accJ[r] *= 2u; }
+					for (int r = 0; r < R; ++r) { acc[r] = first ? 0u : acc[r] * 16u; if (JUMP) accJ[r] *= 2u; }
 				}
 			};
 
@@ -260,19 +325,15 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 				}
 				if (tb >= 32u && tb + SPW - 1u <= l2) {
 #pragma unroll
-					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false);
+					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, k == 0);
 				} else {
 #pragma unroll
-					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true);
+					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true, k == 0);
 				}
 				if (want_ptr) {
 					uint32_t *w = ptr + ((size_t)(stripe * G + tb / SPW) * 32 + lane) * R;
 #pragma unroll
 					for (int r = 0; r < R; ++r) w[r] = acc[r];
-				}
-				if (PACKED) {
-#pragma unroll
-					for (int r = 0; r < R; ++r) acc[r] = 0;   // 4 nibbles per half: the next shift must not spill A's bits into B's half
 				}
 				if (JUMP && want_ptr && ((tb + SPW - 1u) & 31u) == 31u) {
 					uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (tb >> 5)) * 32 + lane) * R;

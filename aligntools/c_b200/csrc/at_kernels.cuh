@@ -190,6 +190,32 @@ __global__ void __launch_bounds__(128) at_traceback_emit(const TraceArgs a)
 	}
 }
 
+// Which byte values occur in a buffer (256-bit set).  The fill kernels switch to their query-profile
+// variant when the shard's targets use at most four distinct symbols.
+__global__ void __launch_bounds__(256) at_symbol_set(const uint8_t *bytes, uint64_t n, uint32_t *set8)
+{
+	__shared__ uint32_t sh[8];
+	if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+	__syncthreads();
+	uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	const uint64_t n16 = n / 16;
+	const uint4 *v = (const uint4 *)bytes;                  // device buffers are 256-byte aligned
+	for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += (uint64_t)gridDim.x * blockDim.x) {
+		const uint4 x = __ldg(v + k);
+		const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+		for (int q = 0; q < 4; ++q)
+#pragma unroll
+			for (int b = 0; b < 4; ++b) { const uint32_t c = (w[q] >> (8 * b)) & 255u; loc[c >> 5] |= 1u << (c & 31u); }
+	}
+	if (blockIdx.x == 0)
+		for (uint64_t k = n16 * 16 + threadIdx.x; k < n; k += blockDim.x) { const uint32_t c = bytes[k]; loc[c >> 5] |= 1u << (c & 31u); }
+#pragma unroll
+	for (int q = 0; q < 8; ++q) if (loc[q]) atomicOr(&sh[q], loc[q]);
+	__syncthreads();
+	if (threadIdx.x < 8 && sh[threadIdx.x]) atomicOr(&set8[threadIdx.x], sh[threadIdx.x]);
+}
+
 // fit+jump: expand the per-pair blacklists into a byte mask aligned with the target bytes.
 __global__ void at_build_jmask(const int32_t *sites, const uint64_t *site_off, const uint64_t *t_off,
                                const uint32_t *t_len, uint32_t n_pairs, uint8_t *jmask)

@@ -180,9 +180,11 @@ struct Shard {
 	DevBuf<uint32_t> d_q_len, d_t_len, d_end_i, d_end_j, d_beg_i, d_beg_j, d_n_ops, d_n_cols, d_counter;
 	DevBuf<int32_t> d_score, d_sites;
 	DevBuf<uint32_t> d_ptr, d_scratch, d_prog; DevBuf<uint8_t> d_bnd, d_scan_tmp; DevBuf<int32_t> d_chain;
+	DevBuf<uint8_t> d_symmap; DevBuf<uint32_t> d_symset;
+	bool prof = false; uint32_t syms = 0;      // query-profile variant of K1: the targets use <= 4 distinct bytes
 	std::vector<uint8_t> h_rclass;
 	std::vector<Chunk> chunks;
-	uint64_t cells = 0, ptr_bytes = 0;
+	uint64_t cells = 0, ptr_bytes = 0, t_span = 0;   // t_span: bytes of d_t that hold the caller's target span
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t evk[2] = {nullptr, nullptr};
 	// last-run timing
@@ -229,7 +231,7 @@ __global__ void at_unpack_2bit(const uint8_t *src, const uint64_t *src_off, cons
 // upload one side (reads or targets) of a shard; rewrites offsets relative to the device buffer
 static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t *src, const uint64_t *off,
                        const uint32_t *len, DevBuf<uint8_t> &d_bytes, DevBuf<uint8_t> &d_packed, DevBuf<uint64_t> &d_off,
-                       DevBuf<uint32_t> &d_len)
+                       DevBuf<uint32_t> &d_len, uint64_t *span_bytes)
 {
 	const uint32_t n = s.n;
 	cudaStream_t st = s.stream;
@@ -248,6 +250,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 		CU(h, raw.alloc(hi - lo + AT_SEQ_SLACK));
 		CU(h, cudaMemcpyAsync(raw.p, src + lo, hi - lo, cudaMemcpyHostToDevice, st));
 		for (uint32_t k = 0; k < n; ++k) rel[k] = off[s.p0 + k] - lo;
+		*span_bytes = hi - lo;
 	} else {                                             // scattered records: repack on the host first
 		std::vector<uint8_t> stage;
 		uint64_t pos = 0;
@@ -259,6 +262,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 		CU(h, raw.alloc(pos + AT_SEQ_SLACK));
 		CU(h, cudaMemcpyAsync(raw.p, stage.data(), pos, cudaMemcpyHostToDevice, st));
 		CU(h, cudaStreamSynchronize(st));
+		*span_bytes = pos;
 	}
 	CU(h, d_off.alloc(n)); CU(h, d_len.alloc(n));
 	CU(h, cudaMemcpyAsync(d_len.p, len + s.p0, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -273,6 +277,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 		h->launches++;
 		CU(h, cudaStreamSynchronize(st));
 		d_src_off.release();
+		*span_bytes = tot;
 	} else {
 		CU(h, cudaMemcpyAsync(d_off.p, rel.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 		CU(h, cudaStreamSynchronize(st));
@@ -299,7 +304,7 @@ static void free_shard(Shard &s)
 	s.d_q_len.release(); s.d_t_len.release(); s.d_end_i.release(); s.d_end_j.release(); s.d_beg_i.release();
 	s.d_beg_j.release(); s.d_n_ops.release(); s.d_n_cols.release(); s.d_counter.release();
 	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_scratch.release(); s.d_bnd.release(); s.d_scan_tmp.release();
-	s.d_prog.release(); s.d_chain.release();
+	s.d_prog.release(); s.d_chain.release(); s.d_symmap.release(); s.d_symset.release();
 	release_chunks(s);
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
 	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
@@ -320,10 +325,44 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	tl_stream = st;
 	const uint32_t n = s.n;
 	int rc;
-	if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len))) return rc;
-	if ((rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len))) return rc;
+	uint64_t q_span = 0;
+	if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span))) return rc;
+	if ((rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span))) return rc;
 	s.d_q2.release(); s.d_t2.release();
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
+	// target alphabet of the shard -> query-profile variant of K1 (affine modes) when it has at most 4 symbols
+	s.prof = false; s.syms = 0;
+	if (b->mode <= AT_FIT && in->encoding == AT_SEQ_2BIT) {
+		uint8_t map[256]; memset(map, 0, sizeof map);
+		map['C'] = 1; map['G'] = 2; map['T'] = 3;
+		s.syms = (uint32_t)'A' | ((uint32_t)'C' << 8) | ((uint32_t)'G' << 16) | ((uint32_t)'T' << 24);
+		CU(h, s.d_symmap.alloc(256));
+		CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, st));
+		CU(h, cudaStreamSynchronize(st));
+		s.prof = !getenv("AT_NO_PROFILE");
+	} else if (b->mode <= AT_FIT && !getenv("AT_NO_PROFILE")) {
+		uint32_t set8[8];
+		CU(h, s.d_symset.alloc(8));
+		CU(h, cudaMemsetAsync(s.d_symset.p, 0, 8 * sizeof(uint32_t), st));
+		// d_t holds the caller's span [lo, hi): every byte of it is a target byte or the gap between records
+		at_symbol_set<<<(int)std::min<uint64_t>(s.dev->sm_count * 8, (s.t_span + 4095) / 4096 + 1), 256, 0, st>>>(s.d_t.p, s.t_span, s.d_symset.p);
+		CU(h, cudaGetLastError());
+		h->launches++;
+		CU(h, cudaMemcpyAsync(set8, s.d_symset.p, sizeof set8, cudaMemcpyDeviceToHost, st));
+		CU(h, cudaStreamSynchronize(st));
+		uint8_t map[256]; memset(map, 0, sizeof map);
+		int nsym = 0; uint32_t syms = 0;
+		for (int c = 0; c < 256; ++c)
+			if (set8[c >> 5] >> (c & 31) & 1u) { if (nsym < 4) { map[c] = (uint8_t)nsym; syms |= (uint32_t)c << (8 * nsym); } ++nsym; }
+		if (nsym >= 1 && nsym <= 4) {
+			// unused codes must not equal any read byte by accident: point them at a used symbol
+			for (int c = nsym; c < 4; ++c) syms |= (syms & 255u) << (8 * c);
+			s.syms = syms; s.prof = true;
+			CU(h, s.d_symmap.alloc(256));
+			CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, st));
+			CU(h, cudaStreamSynchronize(st));
+		}
+	}
 	if (jump) {
 		uint64_t tot_t = 0;
 		for (uint32_t k = 0; k < n; ++k) tot_t += in->t_len[s.p0 + k];
@@ -599,24 +638,25 @@ extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const
 typedef void (*fill2_fn)(const FillArgs2);
 typedef void (*wave_fn)(const WaveArgs);
 
-template <int R> static fill2_fn affine_fn(int kind)
+template <int R, bool PROF> static fill2_fn affine_fn(int kind)
 {
 	switch (kind) {
-	case 0: return at_fill_affine<MODE_GLOBAL, R, false, false>;
-	case 1: return at_fill_affine<MODE_LOCAL, R, false, false>;
-	case 2: return at_fill_affine<MODE_FIT, R, false, false>;
-	case 3: return at_fill_affine<MODE_FIT, R, true, false>;
-	default: return at_fill_affine<MODE_LOCAL, R, false, true>;
+	case 0: return at_fill_affine<MODE_GLOBAL, R, false, false, PROF>;
+	case 1: return at_fill_affine<MODE_LOCAL, R, false, false, PROF>;
+	case 2: return at_fill_affine<MODE_FIT, R, false, false, PROF>;
+	case 3: return at_fill_affine<MODE_FIT, R, true, false, PROF>;
+	default: return at_fill_affine<MODE_LOCAL, R, false, true, PROF>;
 	}
 }
-static fill2_fn affine_kernel(int kind, int R)
+template <bool PROF> static fill2_fn affine_kernel_r(int kind, int R)
 {
 	switch (R) {
-	case 1: return affine_fn<1>(kind); case 2: return affine_fn<2>(kind); case 3: return affine_fn<3>(kind);
-	case 4: return affine_fn<4>(kind); case 5: return affine_fn<5>(kind); case 6: return affine_fn<6>(kind);
-	case 7: return affine_fn<7>(kind); default: return affine_fn<8>(kind);
+	case 1: return affine_fn<1, PROF>(kind); case 2: return affine_fn<2, PROF>(kind); case 3: return affine_fn<3, PROF>(kind);
+	case 4: return affine_fn<4, PROF>(kind); case 5: return affine_fn<5, PROF>(kind); case 6: return affine_fn<6, PROF>(kind);
+	case 7: return affine_fn<7, PROF>(kind); default: return affine_fn<8, PROF>(kind);
 	}
 }
+static fill2_fn affine_kernel(int kind, int R, bool prof) { return prof ? affine_kernel_r<true>(kind, R) : affine_kernel_r<false>(kind, R); }
 template <int MODE> static wave_fn wave_linear_fn(int R)
 {
 	switch (R) {
@@ -666,10 +706,12 @@ static int run_shard(at_batch *b, Shard &s)
 		for (size_t li = 0; li < c.launches.size(); ++li) {
 			Launch &l = c.launches[li];
 			const void *fn = l.kind == LK_WAVE ? (const void *)wave_kernel(b->mode, jump, l.r)
-			                                   : (const void *)affine_kernel(l.kind == LK_PACKED ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode), l.r);
+			                                   : (const void *)affine_kernel(l.kind == LK_PACKED ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode), l.r, s.prof);
 			const int warps = l.kind == LK_WAVE ? AT_WAVE_WARPS : AT_FILL_WARPS;
+			const size_t dyn_smem = l.kind == LK_WAVE ? 0 : fill_smem_bytes(l.r, l.kind == LK_PACKED, s.prof);
+			if (dyn_smem > 48 * 1024) CU(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
 			int occ = 0;
-			CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * warps, 0));
+			CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * warps, dyn_smem));
 			if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, l.r); return AT_E_CUDA; }
 			int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (l.n_jobs() + warps - 1) / warps);
 			if (blocks < 1) blocks = 1;
@@ -692,13 +734,14 @@ static int run_shard(at_batch *b, Shard &s)
 				FillArgs2 fa;
 				fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
 				fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
-				fa.jmask = s.d_jmask.p; fa.jobs = l.d_jobs.p; fa.n_jobs = (uint32_t)l.h_jobs.size();
+				fa.jmask = s.d_jmask.p; fa.symmap = s.d_symmap.p; fa.syms = s.syms;
+				fa.jobs = l.d_jobs.p; fa.n_jobs = (uint32_t)l.h_jobs.size();
 				fa.counter = s.d_counter.p + (l.kind == LK_PACKED ? 16 : 0) + l.r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
 				fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
 				fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
 				fa.want_ptr = b->traceback ? 1 : 0;
 				void *kargs[] = {(void *)&fa};
-				CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warps), kargs, 0, st));
+				CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warps), kargs, dyn_smem, st));
 			}
 			if (dom) CU(h, cudaEventRecord(s.evk[1], st));
 			s.launches++;
