@@ -324,11 +324,16 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					__syncwarp();
 				}
 				if (tb >= 32u && tb + SPW - 1u <= l2) {
+					if (PACKED) {
 #pragma unroll
-					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, k == 0);
+						for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, k == 0);
+					} else {      // int32 lanes: 8 steps per word; unroll by 4 only (instruction-cache footprint)
+#pragma unroll 4
+						for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, false);
+					}
 				} else {
-#pragma unroll
-					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true, k == 0);
+#pragma unroll 1
+					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true, PACKED && k == 0);
 				}
 				if (want_ptr) {
 					uint32_t *w = ptr + ((size_t)(stripe * G + tb / SPW) * 32 + lane) * R;

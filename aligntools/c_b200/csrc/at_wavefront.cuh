@@ -29,6 +29,8 @@
 namespace at {
 
 #define AT_WAVE_WARPS 4
+constexpr int AT_WAVE_UNROLL_AFFINE = 2;     // steps per loop body (instruction-cache footprint, see the loops)
+constexpr int AT_WAVE_UNROLL_OVERLAP = 4, AT_WAVE_UNROLL_EDIT = 8;
 #define AT_PROG_DONE 0xffffffffu
 #define AT_NEGL (-(1 << 30))       // -inf stand-in of the single-plane kernel (scores x4 stay below 2^29)
 
@@ -313,11 +315,13 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 				const uint32_t c = (tb >> 8) + 1u;
 				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
 			}
+			// two steps per loop body: 8 rows x 2 steps already is ~600 instructions; a fully unrolled pointer
+			// word (8 steps) overflows the instruction cache (ncu: stall_no_instruction was the top stall)
 			if (tb >= 32u && tb + 7u <= l2) {
-#pragma unroll
+#pragma unroll AT_WAVE_UNROLL_AFFINE
 				for (uint32_t k = 0; k < 8; ++k) step(tb + k, false);
 			} else {
-#pragma unroll
+#pragma unroll 1
 				for (uint32_t k = 0; k < 8; ++k) step(tb + k, true);
 			}
 			if (want_ptr && (tb >> 3) < G) {
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 {
 	constexpr int RPP = 32 * R;
 	constexpr bool OV = MODE == MODE_OVERLAP;
+	constexpr int UNR = OV ? AT_WAVE_UNROLL_OVERLAP : AT_WAVE_UNROLL_EDIT;
 	struct __align__(16) Smem { WaveRing<false> rg; int cring[64]; int stage[64]; };
 	__shared__ Smem sm_all[AT_WAVE_WARPS];
 	Smem &sm = sm_all[threadIdx.x >> 5];
@@ -538,10 +543,10 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
 			}
 			if (tb >= 32u && tb + 15u <= l2) {
-#pragma unroll
+#pragma unroll UNR
 				for (uint32_t k = 0; k < 16; ++k) step(tb + k, false);
 			} else {
-#pragma unroll
+#pragma unroll 1
 				for (uint32_t k = 0; k < 16; ++k) step(tb + k, true);
 			}
 			if (want_ptr && (tb >> 4) < G) {
