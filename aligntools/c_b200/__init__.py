@@ -30,7 +30,7 @@ EXPORTS = ["at_default_params", "at_strerror", "at_version", "at_create", "at_de
            "at_device_count", "at_launch_count", "at_align_gla", "at_align_local_affine",
            "at_align_fit_affine_jump", "at_align_overlap", "at_edit_dist", "at_batch_create",
            "at_batch_run", "at_batch_sizes", "at_batch_fetch", "at_batch_free", "at_batch_align",
-           "at_pack_2bit", "at_cigar_to_string"]
+           "at_pack_2bit", "at_cigar_to_string", "at_plan_slices"]
 
 
 class AtError(RuntimeError):
@@ -67,9 +67,15 @@ class _Timing(C.Structure):
 _lib = None
 
 
-def build(force=False, verbose=False):
-    from .build import build as _b
-    return _b(force=force, verbose=verbose)
+def _build_entry(force=False, verbose=False):
+    """Compile libaligntools_b200.so and the C host in-tree (see build.py)."""
+    import importlib
+    mod = importlib.import_module(__name__ + ".build")
+    globals()["build"] = _build_entry        # importing the submodule rebinds the package attribute `build`: undo
+    return mod.build(force=force, verbose=verbose)
+
+
+build = _build_entry
 
 
 def load_library():
@@ -102,8 +108,22 @@ def load_library():
     lib.at_pack_2bit.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
     lib.at_cigar_to_string.restype = C.c_int64
     lib.at_cigar_to_string.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    lib.at_plan_slices.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     _lib = lib
     return lib
+
+
+def plan_slices(q_len, t_len, parts):
+    """Contiguous slices of the batch with nearly equal numbers of DP cells (at_plan_slices):
+    returns parts + 1 cut indices.  The same plan shards a batch over the devices of one handle."""
+    lib = load_library()
+    q_len = np.ascontiguousarray(q_len, dtype=np.uint32)
+    t_len = np.ascontiguousarray(t_len, dtype=np.uint32)
+    cut = np.zeros(parts + 1, dtype=np.uint64)
+    rc = lib.at_plan_slices(q_len.ctypes.data, t_len.ctypes.data, len(q_len), parts, cut.ctypes.data)
+    if rc:
+        raise AtError(rc, "at_plan_slices")
+    return cut
 
 
 @dataclass

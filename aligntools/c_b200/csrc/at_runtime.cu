@@ -598,6 +598,18 @@ static void cut_by_cells(const at_batch_input *in, uint64_t lo, uint64_t hi, siz
 	cut[parts] = hi;
 }
 
+extern "C" int at_plan_slices(const uint32_t *q_len, const uint32_t *t_len, uint64_t n_pairs, uint32_t parts, uint64_t *cut)
+{
+	if (!q_len || !t_len || !cut || parts == 0) return AT_E_ARG;
+	at_batch_input in;
+	memset(&in, 0, sizeof in);
+	in.n_pairs = n_pairs; in.q_len = q_len; in.t_len = t_len;
+	std::vector<uint64_t> c;
+	cut_by_cells(&in, 0, n_pairs, parts, c);
+	for (uint32_t k = 0; k <= parts; ++k) cut[k] = c[k];
+	return AT_OK;
+}
+
 static at_batch *new_batch(at_handle *h, int mode, const at_params *p, uint32_t out_flags, uint64_t n)
 {
 	at_batch *b = new at_batch();

@@ -177,6 +177,13 @@ void at_batch_free(at_batch *b);
 int  at_batch_align(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
                     uint32_t out_flags, at_batch_output *out, at_timing *timing);
 
+/* Sharding plan: cut pairs [0, n) into `parts` CONTIGUOUS slices holding nearly equal
+ * numbers of DP cells (sum of l1*l2).  cut[] receives parts+1 ascending indices, cut[0] = 0 and
+ * cut[parts] = n; slice r is [cut[r], cut[r+1]).  at_batch_create shards a batch over the handle's
+ * devices with exactly this plan; a multi-process host (one rank per GPU) calls it to find each
+ * rank's slice.  Pure host code. */
+int  at_plan_slices(const uint32_t *q_len, const uint32_t *t_len, uint64_t n_pairs, uint32_t parts, uint64_t *cut);
+
 /* Helpers: 2-bit packing (returns number of bytes written = (n+3)/4, or <0 when a symbol
  * is not one of ACGT/acgt... only upper-case ACGT are accepted: the reference compares
  * bytes verbatim, so folding case would change results) and CIGAR rendering. */

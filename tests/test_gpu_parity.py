@@ -260,3 +260,66 @@ def test_pipelined_one_shot_equals_three_call_path(A, aligner, monkeypatch, mode
             aligner.align_arrays(md, opt, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off,
                                  out_flags=1, cigar_cap=16)
         assert e.value.rc == -5
+
+
+@pytest.mark.parametrize("mode", ["global", "local", "fit", "fitjump"])
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"AC", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY"])
+def test_k1_query_profile_and_fallback_variants(A, aligner, oracle_mod, monkeypatch, mode, alphabet):
+    """K1 has two instruction streams: the shared-memory query profile (targets with at most four
+    distinct bytes) and the xor/min fallback (any byte alphabet).  Both must equal the oracle, on
+    int32 lanes and -- local mode, equal target lengths -- on packed s16x2 lanes."""
+    rng = random.Random(4242 + len(alphabet))
+    q, t = [], []
+    for k in range(160):
+        l2 = 180 if k < 120 else rng.randint(40, 260)            # equal l2 -> packed jobs in local mode
+        l1 = rng.randint(1, min(l2, 256))
+        s2 = bytes(rng.choice(alphabet) for _ in range(l2))
+        st = rng.randrange(0, l2 - l1 + 1)
+        s1 = bytes(c if rng.random() > 0.1 else rng.choice(alphabet) for c in s2[st:st + l1])
+        q.append(s1); t.append(s2)
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    prm = dict(m=2, u=-3, o=-4, e=-1, j=-7, jump=(mode == "fitjump"))
+    sites = site_off = None
+    if mode == "fitjump":
+        ss, so = [], [0]
+        for s2 in t:
+            ss += sorted(rng.randrange(len(s2)) for _ in range(rng.choice([0, 2, 6]))); so.append(len(ss))
+        sites = np.array(ss + [0], dtype=np.int32); site_off = np.array(so, dtype=np.uint64)
+    md = "fit" if mode == "fitjump" else mode
+    for no_profile in (False, True):
+        if no_profile:
+            monkeypatch.setenv("AT_NO_PROFILE", "1")
+        else:
+            monkeypatch.delenv("AT_NO_PROFILE", raising=False)
+        check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites, site_off)
+
+
+@pytest.mark.parametrize("mode", ["global", "local", "fit", "fitjump", "overlap", "edit"])
+def test_k2_edge_shapes(A, aligner, oracle_mod, mode):
+    """Stripe-pipelined K2 at its corners: targets shorter than one 32-column hand-off block or one
+    TMA tile, reads of exactly one / one-plus-one stripes, single-column targets, long thin and
+    short wide matrices."""
+    rng = random.Random(31337)
+    if mode.startswith("fit"):      # l1 <= l2, l2 >= 2
+        shapes = [(257, 257), (257, 300), (513, 513), (1000, 1001), (256, 3000), (258, 259), (2049, 2100), (300, 4097)]
+    else:
+        shapes = [(257, 1), (300, 5), (1000, 31), (1000, 32), (1000, 33), (513, 64), (2049, 300), (256, 3000),
+                  (4000, 17), (258, 255), (258, 256), (258, 257), (1, 1), (1, 700), (700, 1), (257, 4097)]
+    q, t = [], []
+    for l1, l2 in shapes:
+        base = bytes(rng.choice(b"ACGT") for _ in range(max(l1, l2)))
+        s1 = bytes(c if rng.random() > 0.07 else rng.choice(b"ACGT") for c in base[:l1])
+        s2 = bytes(c if rng.random() > 0.07 else rng.choice(b"ACGT") for c in base[:l2])
+        q.append(s1); t.append(s2)
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    prm = dict(m=1, u=-2, o=-3, e=-1, j=-5, jump=(mode == "fitjump"))
+    sites = site_off = None
+    if mode == "fitjump":
+        ss, so = [], [0]
+        for s2 in t:
+            ss += sorted(rng.randrange(len(s2)) for _ in range(4)); so.append(len(ss))
+        sites = np.array(ss + [0], dtype=np.int32); site_off = np.array(so, dtype=np.uint64)
+    md = "fit" if mode == "fitjump" else mode
+    check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites, site_off)
