@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU (C2 = 1 Mi)")
     ap.add_argument("--ref-pairs", type=int, default=4096, help="pairs per step of the --impl reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=6000, help="pairs timed for cpu_baseline (about 15 s on one core)")
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="pairs timed for cpu_baseline (about 14 s on one core)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
