@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaligntools_b200.so")
+LIB_PATH = os.environ.get("AT_LIB_PATH") or os.path.join(HERE, "libaligntools_b200.so")   # AT_LIB_PATH: A/B runs of two builds
 
 MODES = {"global": 0, "local": 1, "fit": 2, "overlap": 3, "edit": 4}
 OUT_CIGAR, OUT_ALN = 1, 2

@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -36,11 +37,16 @@ struct at_device {
 	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // at_batch_align's pipeline streams (created on first use)
 };
 
+struct at_batch;
 struct at_handle {
 	std::vector<at_device> devs;
 	std::string err;
 	std::mutex mu;
 	std::atomic<uint64_t> launches{0};
+	// at_batch_align's pipeline: one workspace per (device, worker), kept for the life of the handle so
+	// that after the first call a pipelined batch makes no CUDA allocator call at all
+	std::vector<at_batch *> pipe_ws;
+	std::mutex align_mu;
 };
 
 static void set_err(at_handle *h, const char *fmt, ...)
@@ -76,6 +82,9 @@ extern "C" const char *at_strerror(int rc)
 
 extern "C" const char *at_version(void) { return "aligntools-b200 0.1 (sm_100a)"; }
 
+__global__ void at_unpack_2bit(const uint8_t *src, const uint64_t *src_off, const uint64_t *dst_off,
+                               const uint32_t *len, uint32_t n_pairs, uint8_t *dst);
+
 extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
 {
 	if (!out) return AT_E_ARG;
@@ -97,15 +106,25 @@ extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
 			uint64_t keep = UINT64_MAX;      // keep freed blocks cached in the pool (trimmed in at_destroy)
 			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 		}
+		// The helper kernels ask for the same (maximal) shared-memory carve-out as the fill kernels: an
+		// SM runs kernels of different carve-outs only one after the other, so without this every small
+		// kernel of the pipelined path would wait for a persistent fill grid of another stream to drain.
+		const void *helpers[] = {(const void *)at_traceback_walk, (const void *)at_traceback_emit, (const void *)at_scan_offsets,
+		                         (const void *)at_symbol_set, (const void *)at_build_jmask, (const void *)at_unpack_2bit};
+		for (const void *fn : helpers) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		h->devs.push_back(d);
 	}
 	*out = h;
 	return AT_OK;
 }
 
+extern "C" void at_batch_free(at_batch *b);
+
 extern "C" void at_destroy(at_handle *h)
 {
 	if (!h) return;
+	for (at_batch *ws : h->pipe_ws) if (ws) at_batch_free(ws);
+	h->pipe_ws.clear();
 	for (auto &d : h->devs) {
 		cudaSetDevice(d.id);
 		if (d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
@@ -126,16 +145,45 @@ extern "C" uint64_t at_launch_count(const at_handle *h) { return h ? h->launches
 // the next batch without going back to the driver.  tl_stream is the calling shard's stream.
 static thread_local cudaStream_t tl_stream = nullptr;
 
+// A shard (in the pipelined one-shot path: a worker's workspace) keeps the blocks it releases in a
+// small cache and reuses them for its next allocations, so a steady-state sub-slice makes NO call into
+// the CUDA allocator: cudaMallocAsync / cudaFreeAsync from several streams make the pool insert
+// cross-stream dependencies (or map new memory), which coupled the pipeline workers' streams.
+struct BufCache {
+	struct Blk { void *p; size_t bytes; };
+	std::vector<Blk> free_blocks;
+	void *take(size_t bytes) {
+		size_t best = SIZE_MAX;
+		for (size_t k = 0; k < free_blocks.size(); ++k)
+			if (free_blocks[k].bytes >= bytes && free_blocks[k].bytes <= 4 * bytes + 4096 &&
+			    (best == SIZE_MAX || free_blocks[k].bytes < free_blocks[best].bytes)) best = k;
+		if (best == SIZE_MAX) return nullptr;
+		void *p = free_blocks[best].p;
+		last_bytes = free_blocks[best].bytes;
+		free_blocks.erase(free_blocks.begin() + best);
+		return p;
+	}
+	size_t last_bytes = 0;
+	void give(void *p, size_t bytes) { free_blocks.push_back(Blk{p, bytes}); }
+	void flush(cudaStream_t st) { for (auto &b : free_blocks) cudaFreeAsync(b.p, st); free_blocks.clear(); }
+};
+static thread_local BufCache *tl_cache = nullptr;
+
 template <class T> struct DevBuf {
-	T *p = nullptr; size_t n = 0;
+	T *p = nullptr; size_t n = 0; size_t bytes = 0;
 	cudaError_t alloc(size_t count) {
 		if (count <= n && p) return cudaSuccess;
 		release();
-		cudaError_t e = cudaMallocAsync((void **)&p, std::max<size_t>(count, 1) * sizeof(T), tl_stream);
-		if (e == cudaSuccess) n = count; else { p = nullptr; cudaGetLastError(); }
+		const size_t want = std::max<size_t>(count, 1) * sizeof(T);
+		if (tl_cache) { if (void *q = tl_cache->take(want)) { p = (T *)q; bytes = tl_cache->last_bytes; n = bytes / sizeof(T); return cudaSuccess; } }
+		cudaError_t e = cudaMallocAsync((void **)&p, want, tl_stream);
+		if (e == cudaSuccess) { n = count; bytes = want; } else { p = nullptr; cudaGetLastError(); }
 		return e;
 	}
-	void release() { if (p) cudaFreeAsync(p, tl_stream); p = nullptr; n = 0; }
+	void release() {
+		if (p) { if (tl_cache) tl_cache->give(p, bytes); else cudaFreeAsync(p, tl_stream); }
+		p = nullptr; n = 0; bytes = 0;
+	}
 };
 
 static const int MAXR = 8;
@@ -182,6 +230,8 @@ struct Shard {
 	DevBuf<uint32_t> d_ptr, d_scratch, d_prog; DevBuf<uint8_t> d_bnd, d_scan_tmp; DevBuf<int32_t> d_chain;
 	DevBuf<uint8_t> d_symmap; DevBuf<uint32_t> d_symset;
 	bool prof = false; uint32_t syms = 0;      // query-profile variant of K1: the targets use <= 4 distinct bytes
+	BufCache cache;                            // released device blocks, reused by this shard's next allocations
+	bool workspace = false;                    // pipeline workspace: reused for many sub-slices, buffers get head-room
 	std::vector<uint8_t> h_rclass;
 	std::vector<Chunk> chunks;
 	uint64_t cells = 0, ptr_bytes = 0, t_span = 0;   // t_span: bytes of d_t that hold the caller's target span
@@ -298,6 +348,7 @@ static void release_chunks(Shard &s)
 static void free_shard(Shard &s)
 {
 	if (s.dev) { cudaSetDevice(s.dev->id); tl_stream = s.stream; }
+	tl_cache = &s.cache;
 	s.d_q.release(); s.d_t.release(); s.d_jmask.release(); s.d_rclass.release(); s.d_end_state.release();
 	s.d_q2.release(); s.d_t2.release();
 	s.d_q_off.release(); s.d_t_off.release(); s.d_site_off.release();
@@ -308,6 +359,8 @@ static void free_shard(Shard &s)
 	release_chunks(s);
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
 	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
+	s.cache.flush(s.stream);
+	tl_cache = nullptr;
 }
 
 extern "C" void at_batch_free(at_batch *b)
@@ -323,12 +376,24 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, cudaSetDevice(s.dev->id));
 	cudaStream_t st = s.stream;
 	tl_stream = st;
+	tl_cache = &s.cache;
 	const uint32_t n = s.n;
 	int rc;
+	// AT_PIPE_TRACE=2: host timeline of this function's phases (ms since entry) on stderr
+	static const bool trace_setup = getenv("AT_PIPE_TRACE") && atoi(getenv("AT_PIPE_TRACE")) >= 2;
+	const auto t_enter = std::chrono::steady_clock::now();
+	std::string tl;
+	auto mark = [&](const char *what) {
+		if (!trace_setup) return;
+		char buf[64];
+		snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
+		tl += buf;
+	};
 	uint64_t q_span = 0;
 	if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span))) return rc;
 	if ((rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span))) return rc;
 	s.d_q2.release(); s.d_t2.release();
+	mark("upload");
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
 	// target alphabet of the shard -> query-profile variant of K1 (affine modes) when it has at most 4 symbols
 	s.prof = false; s.syms = 0;
@@ -382,6 +447,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		}
 		(void)tot_t;
 	}
+	mark("alphabet+jmask");
 	// per-pair class, result arrays
 	s.h_rclass.resize(n);
 	s.cells = 0;
@@ -398,17 +464,32 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, cudaMemsetAsync(s.d_beg_j.p, 0, n * sizeof(uint32_t), st));
 	CU(h, s.d_counter.alloc(64));
 
+	mark("results");
 	// ---- chunking by pointer-arena budget ----
+	// The whole shard's pointer blocks in one chunk if they fit the arena this shard already owns (a
+	// pipeline workspace after its first sub-slice); otherwise ask the driver what is free.
+	// cudaMemGetInfo is kept off the steady-state path: with other threads driving the device it was
+	// seen to block for tens of milliseconds.
+	uint64_t need_words = 0;
+	auto pair_words = [&](uint32_t k) -> uint64_t {
+		const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
+		return b->traceback ? ptr_words_of(b->mode, jump, l1, l2) + 64ull * rclass_of(l1) : 0;   // + rounding slack of the packed layout
+	};
+	for (uint32_t k = 0; k < n; ++k) need_words += pair_words(k);
 	size_t free_b = 0, total_b = 0;
-	CU(h, cudaMemGetInfo(&free_b, &total_b));
-	{   // blocks cached in the stream-ordered pool are reusable by this batch: count them as free
+	const bool owned = need_words <= s.d_ptr.n && !getenv("AT_PTR_BUDGET_MB");
+	if (!owned && need_words) {
+		CU(h, cudaMemGetInfo(&free_b, &total_b));
+		// blocks cached in the stream-ordered pool are reusable by this batch: count them as free
 		cudaMemPool_t pool; uint64_t reserved = 0, used = 0;
 		if (cudaDeviceGetDefaultMemPool(&pool, s.dev->id) == cudaSuccess &&
 		    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
 		    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
 			free_b += (size_t)(reserved - used);
+		free_b += s.d_ptr.bytes;      // the arena this shard holds is re-sized, not added to
 	}
-	uint64_t budget_words = (uint64_t)(free_b * 0.45) / 4;
+	uint64_t budget_words = owned ? std::max<uint64_t>(s.d_ptr.n, 1) : (uint64_t)(free_b * 0.45) / 4;
+	if (!need_words) budget_words = UINT64_MAX;
 	if (const char *env = getenv("AT_PTR_BUDGET_MB")) budget_words = (uint64_t)atoll(env) * (1ull << 20) / 4;
 	// packed s16x2 lanes (two pairs per warp): local mode, scores x8 must fit int16, 8|m-u| < 256 (symbols are << 8)
 	const int64_t maxabs = std::max<int64_t>({llabs((long long)b->prm.m), llabs((long long)b->prm.u), llabs((long long)b->prm.o), llabs((long long)b->prm.e), 1});
@@ -422,8 +503,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		Chunk cur; cur.k0 = 0;
 		uint64_t words = 0;
 		for (uint32_t k = 0; k < n; ++k) {
-			const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
-			const uint64_t w = b->traceback ? ptr_words_of(b->mode, jump, l1, l2) + 64ull * rclass_of(l1) : 0;   // + rounding slack of the packed layout
+			const uint64_t w = pair_words(k);
 			if (w > budget_words) { set_err(h, "pair %llu needs %llu MB of traceback pointers; arena budget is %llu MB",
 			                                (unsigned long long)(s.p0 + k), (unsigned long long)(w >> 18), (unsigned long long)(budget_words >> 18)); return AT_E_NOMEM; }
 			if (words + w > budget_words && k > cur.k0) {
@@ -434,6 +514,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		}
 		cur.k1 = n; s.chunks.push_back(std::move(cur));
 	}
+	mark("meminfo+chunks");
 	s.ptr_bytes = 0;
 	const bool linear = b->mode >= AT_OVERLAP;          // single-plane modes run on K2 at every length
 	uint64_t max_bnd_elems = 0, max_prog_words = 0;
@@ -541,6 +622,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		}
 		CU(h, cudaStreamSynchronize(st));
 	}
+	mark("plan+jobs");
 	if (max_bnd_elems && s.d_bnd.alloc(max_bnd_elems * (linear ? sizeof(int32_t) : sizeof(int4)) + 64) != cudaSuccess) { set_err(h, "stripe boundary slabs of %llu MB", (unsigned long long)((max_bnd_elems * (linear ? 4 : 16)) >> 20)); return AT_E_NOMEM; }
 	if (!max_bnd_elems) CU(h, s.d_bnd.alloc(64));
 	CU(h, s.d_prog.alloc(max_prog_words + 1));
@@ -554,11 +636,13 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, cudaMemcpyAsync(s.d_rclass.p, s.h_rclass.data(), n, cudaMemcpyHostToDevice, st));
 	CU(h, cudaStreamSynchronize(st));
 	if (max_chunk_words) {
-		cudaError_t e = s.d_ptr.alloc(max_chunk_words);
+		cudaError_t e = s.d_ptr.alloc(max_chunk_words + (s.workspace && max_chunk_words > s.d_ptr.n ? max_chunk_words / 16 : 0));
 		if (e != cudaSuccess) { set_err(h, "pointer arena of %llu MB: %s", (unsigned long long)(max_chunk_words >> 18), cudaGetErrorString(e)); return AT_E_NOMEM; }
 	}
 	for (auto &e : s.ev) if (!e) CU(h, cudaEventCreate(&e));
 	for (auto &e : s.evk) if (!e) CU(h, cudaEventCreate(&e));
+	mark("arena");
+	if (trace_setup) fprintf(stderr, "[at setup] pairs %u:%s\n", n, tl.c_str());
 	return AT_OK;
 }
 
@@ -690,12 +774,16 @@ static wave_fn wave_kernel(int mode, bool jump, int R)
 
 struct CastU64 { __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; } };
 
-static int run_shard(at_batch *b, Shard &s)
+// `fills_done` (optional) is called once, right after the fill kernels of the shard's LAST chunk have
+// completed on the device: the pipelined one-shot path hands the SMs to the next sub-slice there, so
+// its fill overlaps this sub-slice's traceback kernels and host round trips.
+static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_done = nullptr)
 {
 	at_handle *h = b->h;
 	CU(h, cudaSetDevice(s.dev->id));
 	cudaStream_t st = s.stream;
 	tl_stream = st;
+	tl_cache = &s.cache;
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
 	s.fill_ms = s.tb_ms = s.dev_ms = s.domk_ms = 0; s.domk_cells = 0; s.launches = 0;
 	// dominant (most cells) fill launch of the whole shard -> per-launch timing for the roofline
@@ -759,6 +847,7 @@ static int run_shard(at_batch *b, Shard &s)
 			s.launches++;
 		}
 		CU(h, cudaEventRecord(e_fill, st));
+		if (fills_done && ci + 1 == s.chunks.size()) { CU(h, cudaEventSynchronize(e_fill)); (*fills_done)(); }
 		if (b->traceback) {
 			TraceArgs ta;
 			ta.q = s.d_q.p; ta.q_off = s.d_q_off.p; ta.q_len = s.d_q_len.p;
@@ -774,16 +863,22 @@ static int run_shard(at_batch *b, Shard &s)
 			at_traceback_walk<<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
-			// inclusive scans (CUB) of n_ops / n_cols into offsets[1..nc]; offsets[0] = 0
-			size_t tmp_bytes = 0;
-			cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_ops(s.d_n_ops.p + c.k0, CastU64());
-			cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_cols(s.d_n_cols.p + c.k0, CastU64());
-			CU(h, cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
-			CU(h, s.d_scan_tmp.alloc(tmp_bytes + 16));
-			CU(h, cudaMemsetAsync(c.d_ops_off.p, 0, sizeof(uint64_t), st));
-			CU(h, cudaMemsetAsync(c.d_cols_off.p, 0, sizeof(uint64_t), st));
-			CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
-			CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_cols, c.d_cols_off.p + 1, (int)nc, st));
+			// exclusive offsets of n_ops / n_cols: offsets[0] = 0, offsets[1..nc] inclusive sums
+			if (s.workspace && nc <= (1u << 18)) {      // pipelined path: must be able to run beside another stream's fill
+				at_scan_offsets<<<2, 1024, 0, st>>>(s.d_n_ops.p + c.k0, s.d_n_cols.p + c.k0, nc, c.d_ops_off.p, c.d_cols_off.p);
+				CU(h, cudaGetLastError());
+				s.launches++;
+			} else {
+				size_t tmp_bytes = 0;
+				cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_ops(s.d_n_ops.p + c.k0, CastU64());
+				cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_cols(s.d_n_cols.p + c.k0, CastU64());
+				CU(h, cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
+				CU(h, s.d_scan_tmp.alloc(tmp_bytes + 16));
+				CU(h, cudaMemsetAsync(c.d_ops_off.p, 0, sizeof(uint64_t), st));
+				CU(h, cudaMemsetAsync(c.d_cols_off.p, 0, sizeof(uint64_t), st));
+				CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
+				CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_cols, c.d_cols_off.p + 1, (int)nc, st));
+			}
 			uint64_t tot[2] = {0, 0};
 			CU(h, cudaMemcpyAsync(&tot[0], c.d_ops_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 			CU(h, cudaMemcpyAsync(&tot[1], c.d_cols_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -922,6 +1017,8 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
                            at_batch_output *out, at_timing *timing, uint64_t total_cells)
 {
 	const size_t nd = h->devs.size();
+	std::lock_guard<std::mutex> one_at_a_time(h->align_mu);
+	if (h->pipe_ws.size() < nd * AT_PIPE_STREAMS) h->pipe_ws.resize(nd * AT_PIPE_STREAMS, nullptr);
 	std::vector<uint64_t> dcut;
 	cut_by_cells(in, 0, in->n_pairs, nd, dcut);
 	std::vector<PipeSlice> slices;
@@ -958,8 +1055,9 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 
 	std::mutex mu; std::condition_variable cv;
 	std::atomic<int> failed{0};
-	// one sub-slice at a time owns a device's SMs: concurrent persistent fills would share them, finish
-	// together and leave the GPU idle while all workers prepare their next sub-slice in lockstep
+	// one sub-slice's FILL at a time owns a device's SMs: concurrent persistent fills would share them,
+	// finish together and leave the GPU idle while all workers prepare their next sub-slice in lockstep.
+	// The lock is handed on as soon as the fill has completed, so the next fill overlaps the traceback.
 	std::vector<std::mutex> run_mu(nd);
 	std::vector<std::atomic<size_t>> next(nd);
 	for (auto &x : next) x = 0;
@@ -972,10 +1070,13 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 	auto worker = [&](size_t d, int w) {
 		at_device &dv = h->devs[d];
 		Acc &a = acc[d * AT_PIPE_STREAMS + w];
-		// one workspace per worker: the sequence buffers, pointer arena and scratch of the first
-		// sub-slice are reused by the later ones (no allocator traffic inside the pipeline)
-		at_batch *b = new_batch(h, mode, p, out_flags, 0);
-		b->shards.resize(1);
+		// one workspace per worker, owned by the handle: the sequence buffers, pointer arena and scratch
+		// are reused by every sub-slice of this and of later calls (no allocator traffic in the pipeline)
+		at_batch *&slot = h->pipe_ws[d * AT_PIPE_STREAMS + w];
+		if (!slot) { slot = new_batch(h, mode, p, out_flags, 0); slot->shards.resize(1); }
+		at_batch *b = slot;
+		b->mode = mode; b->prm = *p; b->out_flags = out_flags;
+		b->traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
 		for (;;) {
 			const size_t k = next[d].fetch_add(1);
 			if (k >= per_dev[d].size() || failed.load()) break;
@@ -988,11 +1089,15 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 			if (in->site_off) sub.site_off = in->site_off + sl.lo;
 			b->n = sub.n_pairs;
 			Shard &s = b->shards[0];
-			s.dev = &dv; s.stream = dv.pipe[w]; s.p0 = 0; s.p1 = sub.n_pairs; s.n = (uint32_t)sub.n_pairs; s.out_base = sl.lo;
+			s.dev = &dv; s.stream = dv.pipe[w]; s.workspace = true; s.p0 = 0; s.p1 = sub.n_pairs; s.n = (uint32_t)sub.n_pairs; s.out_base = sl.lo;
 			const double t_a = now_ms();
 			int rc = setup_shard(b, s, &sub);
 			const double t_b = now_ms();
-			if (!rc) { std::lock_guard<std::mutex> own(run_mu[d]); rc = run_shard(b, s); }
+			if (!rc) {
+				std::unique_lock<std::mutex> own(run_mu[d]);
+				const std::function<void()> hand_on = [&] { if (own.owns_lock()) own.unlock(); };
+				rc = run_shard(b, s, &hand_on);
+			}
 			const double t_c = now_ms();
 			uint64_t to = 0, tc = 0;
 			if (!rc) for (auto &c : s.chunks) { to += c.tot_ops; tc += c.tot_cols; }
@@ -1017,7 +1122,6 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 			if (s.domk_cells > a.domc) { a.domc = s.domk_cells; a.domk = s.domk_ms; }
 			if (rc) { std::lock_guard<std::mutex> lk(mu); failed = rc; cv.notify_all(); break; }
 		}
-		if (b->shards[0].dev) at_batch_free(b); else delete b;
 	};
 	std::vector<std::thread> th;
 	for (size_t d = 0; d < nd; ++d)

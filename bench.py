@@ -264,6 +264,8 @@ def main():
             dt = time.perf_counter() - t1
             if k:
                 e2e_times.append(dt)
+            if os.environ.get("AT_BENCH_VERBOSE"):
+                print(f"[bench] e2e iteration {k}: {1e3 * dt:.2f} ms", file=sys.stderr, flush=True)
             d2h = r2.score.nbytes + 4 * r2.end_i.nbytes + (r2.cigar_off.nbytes - 8) + int(r2.cigar_off[-1]) * 4
         e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
         if use_dist:
