@@ -106,6 +106,10 @@ struct RunWriter {
 };
 
 // One thread per pair: chase the pointers once, leave the reversed CIGAR in the pair's scratch slot.
+// BESIDE_FILL only makes two distinct functions: the <true> instances are given the fill kernels'
+// shared-memory carve-out (they run beside another stream's persistent fill grid in the pipelined
+// path), the <false> instances keep the default carve-out -- the walk lives on L1 hits.
+template <bool BESIDE_FILL>
 __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 
 // One warp per pair: reverse the scratch ops into the dense CIGAR and, on request, replay them
 // forward over the two sequences to write the gapped strings r1 / r2 (coalesced).
+template <bool BESIDE_FILL>
 __global__ void __launch_bounds__(128) at_traceback_emit(const TraceArgs a)
 {
 	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -100,6 +100,9 @@ extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
 		cudaDeviceProp prop;
 		if (cudaGetDeviceProperties(&prop, id) != cudaSuccess || prop.major < 10) { delete h; return AT_E_CUDA; }
 		at_device d; d.id = id; d.sm_count = prop.multiProcessorCount;
+		// host threads waiting for the device yield their core between polls: the pipelined path runs three
+		// workers per GPU, and a multi-rank job (one process per GPU) must not starve them on a small host
+		if (cudaSetDevice(id) == cudaSuccess && cudaSetDeviceFlags(cudaDeviceScheduleYield) != cudaSuccess) cudaGetLastError();
 		if (cudaSetDevice(id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return AT_E_CUDA; }
 		cudaMemPool_t pool;
 		if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
@@ -109,7 +112,7 @@ extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
 		// The helper kernels ask for the same (maximal) shared-memory carve-out as the fill kernels: an
 		// SM runs kernels of different carve-outs only one after the other, so without this every small
 		// kernel of the pipelined path would wait for a persistent fill grid of another stream to drain.
-		const void *helpers[] = {(const void *)at_traceback_walk, (const void *)at_traceback_emit, (const void *)at_scan_offsets,
+		const void *helpers[] = {(const void *)at_traceback_walk<true>, (const void *)at_traceback_emit<true>, (const void *)at_scan_offsets,
 		                         (const void *)at_symbol_set, (const void *)at_build_jmask, (const void *)at_unpack_2bit};
 		for (const void *fn : helpers) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		h->devs.push_back(d);
@@ -860,7 +863,8 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			ta.scratch = s.d_scratch.p; ta.scratch_off = c.d_scratch_off.p;
 			ta.cigar = nullptr; ta.aln1 = nullptr; ta.aln2 = nullptr;
 			ta.mode = b->mode; ta.jump = jump ? 1 : 0;
-			at_traceback_walk<<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
+			if (s.workspace) at_traceback_walk<true><<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
+			else at_traceback_walk<false><<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
 			// exclusive offsets of n_ops / n_cols: offsets[0] = 0, offsets[1..nc] inclusive sums
@@ -889,7 +893,8 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			if (want_aln) { if (c.d_aln1.alloc(c.tot_cols + 1) != cudaSuccess || c.d_aln2.alloc(c.tot_cols + 1) != cudaSuccess) { set_err(h, "alignment buffer"); return AT_E_NOMEM; } }
 			ta.cigar = want_cig ? c.d_cigar.p : nullptr;
 			ta.aln1 = want_aln ? c.d_aln1.p : nullptr; ta.aln2 = want_aln ? c.d_aln2.p : nullptr;
-			at_traceback_emit<<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
+			if (s.workspace) at_traceback_emit<true><<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
+			else at_traceback_emit<false><<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
 		}
