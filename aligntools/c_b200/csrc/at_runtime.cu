@@ -1014,7 +1014,7 @@ extern "C" int at_batch_fetch(at_batch *b, at_batch_output *out)
 #define AT_PIPE_STREAMS 3
 static uint64_t env_u64(const char *name, uint64_t dflt) { const char *e = getenv(name); return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : dflt; }
 static uint64_t pipe_min_cells() { return env_u64("AT_PIPE_MIN_CELLS", 1ull << 31); }      // below this a batch is not worth cutting up
-static uint64_t pipe_slice_cells() { return env_u64("AT_PIPE_SLICE_CELLS", 1ull << 32); }  // target cells per sub-slice (2-3 ms of fill)
+static uint64_t pipe_slice_cells() { return env_u64("AT_PIPE_SLICE_CELLS", 1ull << 33); }  // target cells per full-size sub-slice (about 5 ms of fill)
 
 struct PipeSlice { uint64_t lo = 0, hi = 0; size_t dev = 0; uint64_t tot_ops = 0, tot_cols = 0; bool known = false; };
 
@@ -1032,14 +1032,17 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 		if (dcut[d + 1] == dcut[d]) continue;
 		uint64_t cells = 0;
 		for (uint64_t k = dcut[d]; k < dcut[d + 1]; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
-		size_t parts = (size_t)std::max<uint64_t>(1, cells / pipe_slice_cells());
-		parts = std::min<size_t>(parts, 64);
-		parts = std::min<size_t>(parts, (size_t)(dcut[d + 1] - dcut[d]));
+		// graduated sub-slices: quarter-size units, grouped 1, 2, 4, 4, 4, ... so that the first kernel starts
+		// early (short first upload) while the bulk runs in full-size sub-slices (fewer kernel tails)
+		size_t units = (size_t)std::max<uint64_t>(1, 4 * cells / pipe_slice_cells());
+		units = std::min<size_t>(units, 256);
+		units = std::min<size_t>(units, (size_t)(dcut[d + 1] - dcut[d]));
 		std::vector<uint64_t> cut;
-		cut_by_cells(in, dcut[d], dcut[d + 1], parts, cut);
-		for (size_t k = 0; k < parts; ++k) {
-			if (cut[k + 1] == cut[k]) continue;
-			PipeSlice sl; sl.lo = cut[k]; sl.hi = cut[k + 1]; sl.dev = d;
+		cut_by_cells(in, dcut[d], dcut[d + 1], units, cut);
+		for (size_t u0 = 0, step = 1; u0 < units; u0 += step, step = std::min<size_t>(2 * step, 4)) {
+			const size_t u1 = std::min(units, u0 + step);
+			if (cut[u1] == cut[u0]) continue;
+			PipeSlice sl; sl.lo = cut[u0]; sl.hi = cut[u1]; sl.dev = d;
 			per_dev[d].push_back(slices.size());
 			slices.push_back(sl);
 		}
