@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.idx), "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -78,9 +78,9 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +90,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if t_begin is None or (t_begin <= ts <= t_end + 0.12)]
+        if not inside:                       # region shorter than one sampling period: take the sample nearest to it
+            inside = [ln for ts, ln in self.lines[-1:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -176,7 +179,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU (C2 = 1 Mi)")
@@ -217,11 +220,11 @@ def main():
 
     # ---------------- value: inputs resident in HBM, device-timed ----------------
     batch = al.batch("local", opt, q, qo, ql, t, to, tl, out_flags=A.OUT_CIGAR)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs a moment to start: begin before the warm-up, keep only the timed region
     for _ in range(args.warmup):
         batch.run()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     dev_ms, fill_ms, tb_ms, launches, kern_ms = 0.0, 0.0, 0.0, 0, []
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -229,8 +232,9 @@ def main():
         dev_ms += tm.device_ms; fill_ms += tm.fill_ms; tb_ms += tm.traceback_ms; launches += tm.launches
         kern_ms.append(tm.fill_kernel_ms)
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
+    t_end = time.perf_counter()
+    wall_ms = (t_end - t0) * 1e3
+    clocks = sampler.stop(t0, t_end)
     res = batch.fetch()
     cells = tm.cells
     if use_dist:

@@ -72,8 +72,45 @@ def check(al, w, threads, with_cols=True):
     return out
 
 
+def check_bulk(al, w, threads, n_sample, seed=1):
+    """A batch too large to re-run on the CPU (several pointer-arena chunks): run it whole on the GPU,
+    then re-run a random sample of its pairs through the port and compare score, cells and columns."""
+    mode, prm = w["mode"], w["params"]
+    n = len(w["q_len"])
+    b = al.batch(mode, A.Opt(**prm), w["q"], w["q_off"], w["q_len"], w["t"], w["t_off"], w["t_len"],
+                 sites=w["sites"], site_off=w["site_off"], out_flags=A.OUT_CIGAR)
+    tm = b.run()
+    res = b.fetch()
+    b.free()
+    rng = np.random.default_rng(seed)
+    pick = np.unique(np.concatenate([[0, n - 1], rng.integers(0, n, size=n_sample)]))
+    p = oracle.Params(prm["m"], prm["u"], prm["o"], prm["e"], prm["j"], prm["jump"])
+    sites = site_off = None
+    if w["sites"] is not None:
+        so = [0]
+        ss = []
+        for k in pick:
+            ss.append(w["sites"][int(w["site_off"][k]):int(w["site_off"][k + 1])]); so.append(so[-1] + len(ss[-1]))
+        sites = np.concatenate(ss + [np.zeros(1, np.int32)]).astype(np.int32); site_off = np.array(so, dtype=np.uint64)
+    ref = oracle.port_batch(mode, p, w["q"], np.append(w["q_off"][pick], 0).astype(np.uint64), np.ascontiguousarray(w["q_len"][pick]), w["t"],
+                            np.append(w["t_off"][pick], 0).astype(np.uint64), np.ascontiguousarray(w["t_len"][pick]), sites, site_off,
+                            want_aln=True, want_ops=True, threads=threads)
+    bad = 0
+    for x, k in enumerate(pick):
+        ok = int(res.score[k]) == int(ref.score[x]) and int(res.end_i[k]) == int(ref.coords[x, 0]) and int(res.end_j[k]) == int(ref.coords[x, 1])
+        ops = res.cigar_ops(int(k))
+        cols = np.repeat(CODE[ops & 3], (ops >> 4).astype(np.int64)).tobytes()
+        ok = ok and cols == ref.op(x)
+        bad += 0 if ok else 1
+    return {"pairs": n, "cells": int(tm.cells), "gpu_device_ms": tm.device_ms, "gcups": tm.cells / tm.device_ms / 1e6, "ptr_GB": tm.ptr_bytes / 1e9,
+            "sampled_pairs": int(len(pick)), "sample_mismatch": bad}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--c3-bulk", type=int, default=0, help="pairs of a multi-chunk C3 batch (sample-checked)")
+    ap.add_argument("--c4-bulk", type=int, default=0)
+    ap.add_argument("--bulk-sample", type=int, default=48)
     ap.add_argument("--pairs", type=int, default=1 << 20)
     ap.add_argument("--slice", type=int, default=1 << 17)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
@@ -114,8 +151,17 @@ def main():
     if args.c5:
         doc["c5"] = check(al, synth.config5_edit(n_pairs=args.c5), args.threads)
         print("c5", json.dumps(doc["c5"]), flush=True)
+    if args.c3_bulk:
+        doc["c3_bulk"] = check_bulk(al, synth.config3_fit_jump(n_pairs=args.c3_bulk, stream=7), args.threads, args.bulk_sample)
+        print("c3_bulk", json.dumps(doc["c3_bulk"]), flush=True)
+    if args.c4_bulk:
+        doc["c4_bulk"] = check_bulk(al, synth.config4_overlap(n_pairs=args.c4_bulk, stream=7), args.threads, args.bulk_sample)
+        print("c4_bulk", json.dumps(doc["c4_bulk"]), flush=True)
     al.close()
     bad = sum(v for k, v in agg.items() if k.endswith("mismatch"))
+    for c in ("c3_bulk", "c4_bulk"):
+        if c in doc:
+            bad += doc[c]["sample_mismatch"]
     for c in ("c3", "c4", "c5"):
         if c in doc:
             bad += sum(v for k, v in doc[c].items() if k.endswith("mismatch"))
