@@ -13,7 +13,7 @@
 //   * the last row of a stripe (lane 31) is parked in a shared-memory stage, flushed 32 columns
 //     at a time with one coalesced store to the pair's boundary slab (L2 resident, two slabs
 //     alternating by stripe parity) and published with a release of the task's progress word;
-//   * the next stripe polls that word (acquire), pulls the 32-column block with one coalesced
+//   * the next stripe polls that word, pulls the 32-column block with one coalesced
 //     ld.global.cg a block ahead of its use and feeds lane 0 from a shared-memory ring;
 //   * traceback pointers go to HBM exactly as in K1 (nibbles / 2-bit codes in skewed coordinates,
 //     one dense 128*R-byte run per warp flush), so K3 walks both kernels' output.
@@ -77,10 +77,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		             : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
 	} while (!ok);
 }
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+// Progress word of the predecessor stripe.  A relaxed (strong, L2) load, not ld.acquire: the acquire form
+// is followed by CCTL.IVALL -- an invalidation of the whole L1 -- on every poll (ncu: 13 % of all stall
+// samples of the overlap kernel).  It is not needed here: everything read after the flag (boundary blocks,
+// the local-mode chain record) is fetched with ld.global.cg, which bypasses L1, and those loads are issued
+// only after the branch on the flag's value has resolved; the producer orders its st.global.cg stores
+// before the flag with st.release.gpu.
+__device__ __forceinline__ uint32_t ld_progress(const uint32_t *p)
 {
 	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
 __device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
@@ -115,11 +121,11 @@ __device__ __forceinline__ void wait_columns(const uint32_t *prog, uint32_t need
 	if (seen >= need) return;
 	uint32_t v = 0;
 	if (lane == 0) {
-		v = ld_acquire(prog);
-		while (v < need) { __nanosleep(100); v = ld_acquire(prog); }
+		v = ld_progress(prog);
+		while (v < need) { __nanosleep(100); v = ld_progress(prog); }
 	}
 	seen = __shfl_sync(0xffffffffu, v, 0);
-	__syncwarp();                              // orders the other lanes' loads after lane 0's acquire
+	__syncwarp();                              // the other lanes' loads are issued after lane 0 has seen the flag
 }
 
 // =====================================================================================
