@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -30,11 +31,36 @@
 using namespace at;
 
 // ------------------------------------------------------------------ handle ----
+// Large device blocks (the traceback-pointer arena: tens of GB) come from plain cudaMalloc and are kept
+// in a per-device cache for the life of the handle.  The stream-ordered pool maps such a block at about
+// 20 GB/s the first time (seconds for one arena); cudaMalloc takes milliseconds.
+struct BigCache {
+	struct Blk { void *p; size_t bytes; };
+	std::mutex mu;
+	std::vector<Blk> free_blocks;
+	void *take(size_t bytes, size_t *got) {
+		std::lock_guard<std::mutex> g(mu);
+		size_t best = SIZE_MAX;
+		for (size_t k = 0; k < free_blocks.size(); ++k)
+			if (free_blocks[k].bytes >= bytes && free_blocks[k].bytes <= 2 * bytes &&
+			    (best == SIZE_MAX || free_blocks[k].bytes < free_blocks[best].bytes)) best = k;
+		if (best == SIZE_MAX) return nullptr;
+		void *p = free_blocks[best].p; *got = free_blocks[best].bytes;
+		free_blocks.erase(free_blocks.begin() + best);
+		return p;
+	}
+	void give(void *p, size_t bytes) { std::lock_guard<std::mutex> g(mu); free_blocks.push_back(Blk{p, bytes}); }
+	void drop_all() { std::lock_guard<std::mutex> g(mu); for (auto &b : free_blocks) cudaFree(b.p); free_blocks.clear(); }
+	size_t cached_bytes() { std::lock_guard<std::mutex> g(mu); size_t t = 0; for (auto &b : free_blocks) t += b.bytes; return t; }
+};
+static const size_t AT_BIG_BLOCK = 256ull << 20;
+
 struct at_device {
 	int id = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // at_batch_align's pipeline streams (created on first use)
+	std::shared_ptr<BigCache> big = std::make_shared<BigCache>();
 };
 
 struct at_batch;
@@ -132,6 +158,7 @@ extern "C" void at_destroy(at_handle *h)
 		cudaSetDevice(d.id);
 		if (d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
 		for (auto &ps : d.pipe) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
+		d.big->drop_all();
 		cudaMemPool_t pool;
 		if (cudaDeviceGetDefaultMemPool(&pool, d.id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
 	}
@@ -171,21 +198,41 @@ struct BufCache {
 	void flush(cudaStream_t st) { for (auto &b : free_blocks) cudaFreeAsync(b.p, st); free_blocks.clear(); }
 };
 static thread_local BufCache *tl_cache = nullptr;
+static thread_local BigCache *tl_big = nullptr;
 
 template <class T> struct DevBuf {
-	T *p = nullptr; size_t n = 0; size_t bytes = 0;
+	T *p = nullptr; size_t n = 0; size_t bytes = 0; bool big = false;
 	cudaError_t alloc(size_t count) {
 		if (count <= n && p) return cudaSuccess;
 		release();
 		const size_t want = std::max<size_t>(count, 1) * sizeof(T);
+		if (want >= AT_BIG_BLOCK && tl_big) {          // arena-sized: cudaMalloc, cached per device
+			size_t got = 0;
+			void *q = tl_big->take(want, &got);
+			cudaError_t e = cudaSuccess;
+			if (!q) {
+				got = want;
+				e = cudaMalloc(&q, want);
+				if (e != cudaSuccess) { cudaGetLastError(); tl_big->drop_all(); e = cudaMalloc(&q, want); }   // cached blocks may be in the way
+			}
+			if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return e; }
+			p = (T *)q; bytes = got; n = got / sizeof(T); big = true;
+			return cudaSuccess;
+		}
 		if (tl_cache) { if (void *q = tl_cache->take(want)) { p = (T *)q; bytes = tl_cache->last_bytes; n = bytes / sizeof(T); return cudaSuccess; } }
 		cudaError_t e = cudaMallocAsync((void **)&p, want, tl_stream);
+		if (e != cudaSuccess && tl_big) { cudaGetLastError(); tl_big->drop_all(); e = cudaMallocAsync((void **)&p, want, tl_stream); }   // cached arenas may be in the way
 		if (e == cudaSuccess) { n = count; bytes = want; } else { p = nullptr; cudaGetLastError(); }
 		return e;
 	}
 	void release() {
-		if (p) { if (tl_cache) tl_cache->give(p, bytes); else cudaFreeAsync(p, tl_stream); }
-		p = nullptr; n = 0; bytes = 0;
+		if (p) {
+			if (big && tl_big) tl_big->give(p, bytes);
+			else if (big) cudaFree(p);
+			else if (tl_cache) tl_cache->give(p, bytes);
+			else cudaFreeAsync(p, tl_stream);
+		}
+		p = nullptr; n = 0; bytes = 0; big = false;
 	}
 };
 
@@ -350,7 +397,7 @@ static void release_chunks(Shard &s)
 
 static void free_shard(Shard &s)
 {
-	if (s.dev) { cudaSetDevice(s.dev->id); tl_stream = s.stream; }
+	if (s.dev) { cudaSetDevice(s.dev->id); tl_stream = s.stream; tl_big = s.dev->big.get(); }
 	tl_cache = &s.cache;
 	s.d_q.release(); s.d_t.release(); s.d_jmask.release(); s.d_rclass.release(); s.d_end_state.release();
 	s.d_q2.release(); s.d_t2.release();
@@ -363,7 +410,7 @@ static void free_shard(Shard &s)
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
 	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
 	s.cache.flush(s.stream);
-	tl_cache = nullptr;
+	tl_cache = nullptr; tl_big = nullptr;
 }
 
 extern "C" void at_batch_free(at_batch *b)
@@ -379,7 +426,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, cudaSetDevice(s.dev->id));
 	cudaStream_t st = s.stream;
 	tl_stream = st;
-	tl_cache = &s.cache;
+	tl_cache = &s.cache; tl_big = s.dev->big.get();
 	const uint32_t n = s.n;
 	int rc;
 	// AT_PIPE_TRACE=2: host timeline of this function's phases (ms since entry) on stderr
@@ -490,6 +537,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
 			free_b += (size_t)(reserved - used);
 		free_b += s.d_ptr.bytes;      // the arena this shard holds is re-sized, not added to
+		free_b += s.dev->big->cached_bytes();      // arena-sized blocks cached in the handle are dropped on demand
 	}
 	uint64_t budget_words = owned ? std::max<uint64_t>(s.d_ptr.n, 1) : (uint64_t)(free_b * 0.45) / 4;
 	if (!need_words) budget_words = UINT64_MAX;
@@ -786,7 +834,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 	CU(h, cudaSetDevice(s.dev->id));
 	cudaStream_t st = s.stream;
 	tl_stream = st;
-	tl_cache = &s.cache;
+	tl_cache = &s.cache; tl_big = s.dev->big.get();
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
 	s.fill_ms = s.tb_ms = s.dev_ms = s.domk_ms = 0; s.domk_cells = 0; s.launches = 0;
 	// dominant (most cells) fill launch of the whole shard -> per-launch timing for the roofline
