@@ -240,7 +240,7 @@ static const int MAXR = 8;
 static const size_t AT_SEQ_SLACK = 1024;   // K2 stages 256-byte target tiles by TMA: the last tile may run past the last record
 
 // One kernel launch of a chunk: the jobs of one (kernel kind, rows-per-lane) class.
-enum { LK_INT32 = 0, LK_PACKED = 1, LK_WAVE = 2 };
+enum { LK_INT32 = 0, LK_PACKED = 1, LK_WAVE = 2, LK_BITS = 3 };   // LK_BITS: bit-parallel edit distance (K2 task geometry, 1024*r rows per stripe)
 struct Launch {
 	int kind = LK_INT32, r = 1;
 	uint64_t cells = 0;
@@ -249,7 +249,7 @@ struct Launch {
 	std::vector<WaveTask> h_tasks;      // LK_WAVE: (pair, stripe), pair-major
 	DevBuf<WaveTask> d_tasks;
 	uint64_t prog_base = 0;             // first progress word of this launch in Shard::d_prog
-	size_t n_jobs() const { return kind == LK_WAVE ? h_tasks.size() : h_jobs.size(); }
+	size_t n_jobs() const { return kind >= LK_WAVE ? h_tasks.size() : h_jobs.size(); }
 };
 
 struct Chunk {
@@ -280,6 +280,7 @@ struct Shard {
 	DevBuf<uint32_t> d_ptr, d_scratch, d_prog; DevBuf<uint8_t> d_bnd, d_scan_tmp; DevBuf<int32_t> d_chain;
 	DevBuf<uint8_t> d_symmap; DevBuf<uint32_t> d_symset;
 	bool prof = false; uint32_t syms = 0;      // query-profile variant of K1: the targets use <= 4 distinct bytes
+	bool bits = false;                         // bit-parallel edit distance: `-u 1` and reads of <= 8 distinct bytes
 	BufCache cache;                            // released device blocks, reused by this shard's next allocations
 	bool workspace = false;                    // pipeline workspace: reused for many sub-slices, buffers get head-room
 	std::vector<uint8_t> h_rclass;
@@ -497,6 +498,31 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		}
 		(void)tot_t;
 	}
+	// edit -u 1 on a small read alphabet: the bit-parallel kernel (Myers); symmap: read byte -> 0..7, anything else -> 8
+	s.bits = false;
+	if (b->mode == AT_EDIT && b->prm.u == 1 && !getenv("AT_NO_BITPAR")) {
+		uint8_t map[256]; memset(map, 8, sizeof map);
+		int nsym = 0;
+		if (in->encoding == AT_SEQ_2BIT) { map['A'] = 0; map['C'] = 1; map['G'] = 2; map['T'] = 3; nsym = 4; }
+		else {
+			uint32_t set8[8];
+			CU(h, s.d_symset.alloc(8));
+			CU(h, cudaMemsetAsync(s.d_symset.p, 0, 8 * sizeof(uint32_t), st));
+			at_symbol_set<<<(int)std::min<uint64_t>(s.dev->sm_count * 8, (q_span + 4095) / 4096 + 1), 256, 0, st>>>(s.d_q.p, q_span, s.d_symset.p);
+			CU(h, cudaGetLastError());
+			h->launches++;
+			CU(h, cudaMemcpyAsync(set8, s.d_symset.p, sizeof set8, cudaMemcpyDeviceToHost, st));
+			CU(h, cudaStreamSynchronize(st));
+			for (int c = 0; c < 256; ++c)
+				if (set8[c >> 5] >> (c & 31) & 1u) { if (nsym < 8) map[c] = (uint8_t)nsym; ++nsym; }
+		}
+		if (nsym >= 1 && nsym <= 8) {
+			s.bits = true;
+			CU(h, s.d_symmap.alloc(256));
+			CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, st));
+			CU(h, cudaStreamSynchronize(st));
+		}
+	}
 	mark("alphabet+jmask");
 	// per-pair class, result arrays
 	s.h_rclass.resize(n);
@@ -577,7 +603,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 			for (size_t x = 1; x < v.size() && !ragged; ++x) ragged = cells_of(v[x]) != cells_of(v[0]);
 			if (ragged) std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) { return cells_of(x) > cells_of(y); });
 		};
-		Launch l32[MAXR + 1], l16[MAXR + 1], lwv[MAXR + 1];
+		Launch l32[MAXR + 1], l16[MAXR + 1], lwv[MAXR + 1], lbit[MAXR + 1];
 		std::vector<uint32_t> scalar_pairs, wave_pairs, cand;
 		for (uint32_t k = c.k0; k < c.k1; ++k) {
 			const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
@@ -607,12 +633,26 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		by_cells(wave_pairs);
 		c.h_bnd_off.assign(nc, 0);
 		c.bnd_elems = 0; c.prog_words = 0;
+		// bit-parallel edit distance: r = 32-row blocks per lane, 1024*r rows per stripe.  One column step of a
+		// lane is a serial chain through its r blocks, so few long pairs want r = 1 (more stripes in flight);
+		// 4 blocks per lane amortise the per-step overhead once there are tasks for every resident warp.
+		int bits_r = 1;
+		if (s.bits) {
+			const uint64_t warp_slots = (uint64_t)s.dev->sm_count * 8 * AT_WAVE_WARPS;
+			for (int r : {4, 2}) {
+				uint64_t tasks = 0;
+				for (uint32_t k : wave_pairs) tasks += (in->q_len[s.p0 + k] + 1024u * r - 1) / (1024u * r);
+				if (tasks >= 2 * warp_slots) { bits_r = r; break; }
+			}
+		}
 		for (uint32_t k : wave_pairs) {
-			const int r = s.h_rclass[k] & 15;
 			const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
-			const uint32_t n_stripes = (l1 + 32u * r - 1) / (32u * r);
-			for (uint32_t st2 = 0; st2 < n_stripes; ++st2) lwv[r].h_tasks.push_back(WaveTask{k, st2});
-			lwv[r].cells += cells_of(k);
+			const int r = s.bits ? bits_r : (s.h_rclass[k] & 15);
+			const uint32_t rows = s.bits ? 1024u * r : 32u * r;
+			Launch &lw = s.bits ? lbit[r] : lwv[r];
+			const uint32_t n_stripes = (l1 + rows - 1) / rows;
+			for (uint32_t st2 = 0; st2 < n_stripes; ++st2) lw.h_tasks.push_back(WaveTask{k, st2});
+			lw.cells += cells_of(k);
 			if (n_stripes > 1) { c.h_bnd_off[k - c.k0] = c.bnd_elems; c.bnd_elems += 2ull * ((l2 + 4u) & ~3u); }
 		}
 		for (int r = 1; r <= MAXR; ++r) {
@@ -621,6 +661,10 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 			if (!lwv[r].h_tasks.empty()) {
 				lwv[r].kind = LK_WAVE; lwv[r].r = r; lwv[r].prog_base = c.prog_words; c.prog_words += lwv[r].h_tasks.size();
 				c.launches.push_back(std::move(lwv[r]));
+			}
+			if (!lbit[r].h_tasks.empty()) {
+				lbit[r].kind = LK_BITS; lbit[r].r = r; lbit[r].prog_base = c.prog_words; c.prog_words += lbit[r].h_tasks.size();
+				c.launches.push_back(std::move(lbit[r]));
 			}
 		}
 		max_bnd_elems = std::max(max_bnd_elems, c.bnd_elems);
@@ -648,7 +692,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		max_chunk_words = std::max(max_chunk_words, c.ptr_words);
 		s.ptr_bytes += c.ptr_words * 4;
 		for (Launch &l : c.launches) {
-			if (l.kind == LK_WAVE) {
+			if (l.kind >= LK_WAVE) {
 				CU(h, l.d_tasks.alloc(l.h_tasks.size()));
 				CU(h, cudaMemcpyAsync(l.d_tasks.p, l.h_tasks.data(), l.h_tasks.size() * sizeof(WaveTask), cudaMemcpyHostToDevice, st));
 			} else {
@@ -812,6 +856,7 @@ template <int MODE> static wave_fn wave_linear_fn(int R)
 	case 7: return at_wave_linear<MODE, 7>; default: return at_wave_linear<MODE, 8>;
 	}
 }
+static wave_fn bits_kernel(int R) { return R == 1 ? at_wave_edit_bits<1> : (R == 2 ? at_wave_edit_bits<2> : at_wave_edit_bits<4>); }
 static wave_fn wave_kernel(int mode, bool jump, int R)
 {
 	switch (mode) {
@@ -852,14 +897,15 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 		const uint32_t nc = c.k1 - c.k0;
 		CU(h, cudaMemsetAsync(s.d_counter.p, 0, 64 * sizeof(uint32_t), st));
 		if (c.prog_words) CU(h, cudaMemsetAsync(s.d_prog.p, 0, c.prog_words * sizeof(uint32_t), st));
+		if (s.bits && c.bnd_elems) CU(h, cudaMemsetAsync(s.d_bnd.p, 0, c.bnd_elems * sizeof(int32_t), st));   // tagged hand-off words of at_wave_edit_bits
 		CU(h, cudaEventRecord(e_begin, st));
 		if (first) { CU(h, cudaEventRecord(e_first, st)); first = false; }
 		for (size_t li = 0; li < c.launches.size(); ++li) {
 			Launch &l = c.launches[li];
-			const void *fn = l.kind == LK_WAVE ? (const void *)wave_kernel(b->mode, jump, l.r)
+			const void *fn = l.kind == LK_BITS ? (const void *)bits_kernel(l.r) : l.kind == LK_WAVE ? (const void *)wave_kernel(b->mode, jump, l.r)
 			                                   : (const void *)affine_kernel(l.kind == LK_PACKED ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode), l.r, s.prof);
-			const int warps = l.kind == LK_WAVE ? AT_WAVE_WARPS : AT_FILL_WARPS;
-			const size_t dyn_smem = l.kind == LK_WAVE ? 0 : fill_smem_bytes(l.r, l.kind == LK_PACKED, s.prof);
+			const int warps = l.kind >= LK_WAVE ? AT_WAVE_WARPS : AT_FILL_WARPS;
+			const size_t dyn_smem = l.kind >= LK_WAVE ? 0 : fill_smem_bytes(l.r, l.kind == LK_PACKED, s.prof);
 			if (dyn_smem > 48 * 1024) CU(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
 			int occ = 0;
 			CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * warps, dyn_smem));
@@ -868,12 +914,13 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			if (blocks < 1) blocks = 1;
 			const bool dom = (int)ci == dom_chunk && (int)li == dom_launch;
 			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
-			if (l.kind == LK_WAVE) {
+			if (l.kind >= LK_WAVE) {
 				WaveArgs wa;
+				wa.symmap = s.d_symmap.p;
 				wa.q = s.d_q.p; wa.q_off = s.d_q_off.p; wa.q_len = s.d_q_len.p;
 				wa.t = s.d_t.p; wa.t_off = s.d_t_off.p; wa.t_len = s.d_t_len.p;
 				wa.jmask = s.d_jmask.p; wa.tasks = l.d_tasks.p; wa.n_tasks = (uint32_t)l.h_tasks.size();
-				wa.counter = s.d_counter.p + 32 + l.r; wa.prog = s.d_prog.p + l.prog_base;
+				wa.counter = s.d_counter.p + (l.kind == LK_BITS ? 48 : 32) + l.r; wa.prog = s.d_prog.p + l.prog_base;
 				wa.ptr = s.d_ptr.p; wa.ptr_off = c.d_ptr_off.p; wa.pair_base = c.k0;
 				wa.bnd = s.d_bnd.p; wa.bnd_off = c.d_bnd_off.p; wa.chain = s.d_chain.p;
 				wa.score = s.d_score.p; wa.end_i = s.d_end_i.p; wa.end_j = s.d_end_j.p; wa.end_state = s.d_end_state.p;

@@ -51,6 +51,7 @@ struct WaveArgs {
 	int32_t        *score;   uint32_t *end_i;  uint32_t *end_j;  uint8_t *end_state;
 	int             m, u, o, e, jp;
 	int             want_ptr;
+	const uint8_t  *symmap;  // at_wave_edit_bits: byte -> code 0..7 of the shard's READ alphabet, 8 = not in it
 };
 
 // ---- TMA (bulk async copy) + mbarrier + release/acquire helpers ----
@@ -572,6 +573,227 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 			if (OV) { a.score[p] = (capV - gap) / S; a.end_i[p] = l1; a.end_j[p] = capJ; a.end_state[p] = ST_MID; }
 			else { a.score[p] = capV; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = ST_MID; }
 		}
+		__syncwarp();
+	}
+}
+
+// =====================================================================================
+// Bit-parallel edit distance (Myers 1999 / Hyyro 2003 block formulation) for `edit -u 1`, the
+// unit-cost case of src/alignment.h:291-315:  M[i][j] = min(M[i][j-1]+1, M[i-1][j-1]+(eq?0:1),
+// M[i-1][j]+1),  M[i][0] = i,  M[0][j] = j.  Column j of a 32-row block is held as two bit vectors
+// of vertical differences (Pv: +1, Mv: -1); one column step of a block is ~14 logic/add
+// instructions for 32 cells and passes a horizontal difference in {-1,0,+1} to the block below.
+// Same stripe pipeline as the other K2 kernels: lane k owns R consecutive blocks (32*R rows), a
+// stripe is 1024*R rows, the last block's horizontal difference travels to lane k+1 by shuffle.
+// The match vectors Eq[symbol] of a lane's blocks live in a per-warp shared-memory table, rebuilt
+// per task; target tiles come in by TMA as in the other kernels.  Needs a read alphabet of at
+// most 8 distinct bytes (DNA); anything else runs through at_wave_linear<MODE_EDIT>.
+//
+// Stripe hand-off WITHOUT fences: the boundary row is 2 bits per column, so 16 columns and a tag
+// travel in ONE 64-bit word (single-copy atomic): word g of the slab = (stripe + 1) << 32 | the
+// differences of columns 16g+1 .. 16g+16.  The producer's lane 31 stores it with one st.relaxed;
+// the consumer's lane 0 polls the word itself until the tag is its predecessor's.  The slabs are
+// zeroed by the host before every run.  (The release/acquire protocol of the other kernels cost a
+// membar per 32 columns -- 22 % of this kernel's stall samples when it was first written that way.)
+//   score = M[l1][l2] = l1 + sum over j of the horizontal difference at row l1.     SURVEY.md 8(f) #4.
+// =====================================================================================
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p)
+{
+	uint64_t v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+template <int R>
+__global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const WaveArgs a)
+{
+	constexpr int RPP = 1024 * R;                 // rows per stripe
+	constexpr int NSYM = 9;                       // 8 symbols + "matches nothing"
+	struct __align__(16) Smem { uint32_t eq[NSYM][32][R]; WaveRing<false> rg; };
+	__shared__ Smem sm_all[AT_WAVE_WARPS];
+	__shared__ uint8_t symmap_s[256];
+	Smem &sm = sm_all[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	for (int k = threadIdx.x; k < 256; k += blockDim.x) symmap_s[k] = a.symmap[k];
+	if (lane == 0) { mbar_init(&sm.rg.bar[0], 1); mbar_init(&sm.rg.bar[1], 1); fence_proxy_async_smem(); }
+	__syncthreads();
+	uint32_t ring_par = 0;
+
+	for (;;) {
+		uint32_t job = 0;
+		if (lane == 0) job = atomicAdd(a.counter, 1u);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= a.n_tasks) break;
+		const WaveTask tk = a.tasks[job];
+		const uint32_t p = tk.pair, stripe = tk.stripe;
+		const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
+		const uint8_t *__restrict__ q = a.q + a.q_off[p];
+		const uint8_t *tbase = a.t + a.t_off[p];
+		const uint32_t sh = (uint32_t)((uintptr_t)tbase & 15u);
+		const uint8_t *tbase16 = tbase - sh;
+		const uint32_t n_tiles = (l2 + sh + 255u) >> 8;
+		const uint32_t t_last = (l2 + 31u) | 31u;
+		const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
+		const bool last_stripe = stripe + 1 == n_stripes;
+		const uint32_t n_groups = (l2 + 15u) / 16u;                        // words per slab (the host reserves far more)
+		uint64_t *bnd_pair = (uint64_t *)((int *)a.bnd + a.bnd_off[p - a.pair_base]);
+		uint64_t *bnd_out = bnd_pair + (size_t)(stripe & 1u) * n_groups;
+		const uint64_t *bnd_in = bnd_pair + (size_t)((stripe & 1u) ^ 1u) * n_groups;
+		const uint64_t tag_in = (uint64_t)stripe << 32;                    // the predecessor's tag: (stripe - 1) + 1
+		const uint64_t tag_out = (uint64_t)(stripe + 1u) << 32;
+		const uint32_t row0 = stripe * RPP + lane * 32u * R;
+
+		__syncwarp();
+		if (n_tiles > 0) ring_issue<false>(sm.rg, tbase16, nullptr, 0, lane);
+		if (n_tiles > 1) ring_issue<false>(sm.rg, tbase16, nullptr, 1, lane);
+
+		// match vectors of this lane's blocks: bit i of eq[c][lane][r] <=> read[row0 + 32 r + i] == symbol c
+#pragma unroll
+		for (int c = 0; c < NSYM; ++c)
+#pragma unroll
+			for (int r = 0; r < R; ++r) sm.eq[c][lane][r] = 0;
+		for (int r = 0; r < R; ++r)
+			for (uint32_t i = 0; i < 32u; ++i) {
+				const uint32_t ri = row0 + 32u * r + i;
+				if (ri < l1) sm.eq[symmap_s[__ldg(q + ri)]][lane][r] |= 1u << i;
+			}
+		__syncwarp();
+
+		uint32_t Pv[R], Mv[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) { Pv[r] = 0xffffffffu; Mv[r] = 0; }      // M[i][0] = i (:301)
+		// the pair's last row: which lane / block / bit holds it (last stripe only)
+		const uint32_t lr = (l1 - 1) % RPP;
+		const int own_r = (last_stripe && lane == (int)(lr / (32u * R))) ? (int)((lr % (32u * R)) / 32u) : -1;
+		const uint32_t own_b = lr & 31u;
+		int dist = (int)l1;                                                 // M[l1][0]
+
+		// Horizontal differences travel as two bits: hp (+1) and hn (-1).  In a hand-off word column x of a
+		// group has hp at bit 2x and hn at bit 2x+1.
+		// lane 0: the predecessor's word holding the column in hand; lane 31: the word being assembled
+		uint32_t in_bits = 0, in_group = 0xffffffffu, out_bits = 0, pf_group = 0xffffffffu;
+		uint64_t pf_word = 0;                                              // lane 0: next group's word, requested a call ahead
+		auto group_bits = [&](const uint32_t g) -> uint32_t {              // lane 0, stripe > 0: the predecessor's word of group g
+			if (g != in_group) {
+				uint64_t w = g == pf_group ? pf_word : ld_relaxed_u64(bnd_in + g);
+				while ((w & 0xffffffff00000000ull) != tag_in) { __nanosleep(40); w = ld_relaxed_u64(bnd_in + g); }
+				in_bits = (uint32_t)w; in_group = g;
+			}
+			return in_bits;
+		};
+		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
+		// Start lag: follow the predecessor four groups behind, so that the words requested one call ahead
+		// already carry its tag -- a follower on the predecessor's heels pays an L2 round trip per group.
+		if (stripe && lane == 0) {
+			const uint32_t g = min(3u, n_groups - 1u);
+			while ((ld_relaxed_u64(bnd_in + g) & 0xffffffff00000000ull) != tag_in) __nanosleep(200);
+		}
+		__syncwarp();
+
+		uint32_t sP = 0, sN = 0;       // hp / hn leaving the lane's last block (last computed column)
+		// one column of the lane's R blocks; eq[] = match vectors of the column's symbol, (hp, hn) = horizontal
+		// difference entering the first block, replaced by the one leaving the last block
+		auto column = [&](const uint32_t (&eq)[R], uint32_t &hp, uint32_t &hn) {
+#pragma unroll
+			for (int r = 0; r < R; ++r) {
+				uint32_t Eq = eq[r];
+				const uint32_t Xv = Eq | Mv[r];
+				Eq |= hn;
+				const uint32_t Xh = (((Eq & Pv[r]) + Pv[r]) ^ Pv[r]) | Eq;
+				uint32_t Ph = Mv[r] | ~(Xh | Pv[r]);
+				uint32_t Mh = Pv[r] & Xh;
+				if (r == own_r) dist += (int)((Ph >> own_b) & 1u) - (int)((Mh >> own_b) & 1u);
+				const uint32_t op = Ph >> 31, on = Mh >> 31;
+				Ph = (Ph << 1) | hp;
+				Mh = (Mh << 1) | hn;
+				Pv[r] = Mh | ~(Xv | Ph);
+				Mv[r] = Ph & Xv;
+				hp = op; hn = on;
+			}
+		};
+		auto step = [&](const uint32_t t) {                                // any step: range-checked
+			const int j = (int)t - lane;
+			const bool on = j >= 1 && j <= (int)l2;
+			uint32_t hp = __shfl_up_sync(0xffffffffu, sP, 1), hn = __shfl_up_sync(0xffffffffu, sN, 1);
+			if (lane == 0 && on) {
+				if (stripe == 0) { hp = 1; hn = 0; }                               // M[0][j] - M[0][j-1] = 1 (:302)
+				else { const uint32_t w = group_bits(((uint32_t)j - 1u) >> 4) >> (2u * (((uint32_t)j - 1u) & 15u)); hp = w & 1u; hn = (w >> 1) & 1u; }
+			}
+			if (on) {
+				const uint32_t y = (uint32_t)(j - 1) + sh;
+				const uint32_t c = symmap_s[sm.rg.tring[y & 511u]];
+				uint32_t eq[R];
+#pragma unroll
+				for (int r = 0; r < R; ++r) eq[r] = sm.eq[c][lane][r];
+				column(eq, hp, hn);
+				sP = hp; sN = hn;
+				if (lane == 31 && !last_stripe) {
+					out_bits |= (hp | (hn << 1)) << (2u * (((uint32_t)j - 1u) & 15u));
+					if ((((uint32_t)j - 1u) & 15u) == 15u || j == (int)l2) { st_relaxed_u64(bnd_out + (((uint32_t)j - 1u) >> 4), tag_out | out_bits); out_bits = 0; }
+				}
+			}
+		};
+		// 16 in-range steps (tb a multiple of 16, every lane inside the matrix).  Everything that is not on
+		// the serial chain -- shuffle, half a dozen dependent logic ops, next shuffle -- is done up front:
+		// the shared-memory reads, and lane 0's sixteen boundary inputs (column tb is the last one of the
+		// group in hand, tb+1 .. tb+15 open the next group).  Lane 31's columns tb-31 .. tb-16 are exactly one
+		// group: one 64-bit store, no fence.
+		auto steps16 = [&](const uint32_t tb) {
+			uint64_t nw = 0;                                               // lane 0 requests the NEXT call's group now
+			const uint32_t ng = (tb >> 4) + 1u;
+			const bool pf = lane == 0 && stripe && ng < n_groups;
+			if (pf) nw = ld_relaxed_u64(bnd_in + ng);
+			uint32_t eq[16][R];
+#pragma unroll
+			for (int k = 0; k < 16; ++k) {
+				const uint32_t y = (uint32_t)((int)(tb + k) - lane - 1) + sh;
+				const uint32_t c = symmap_s[sm.rg.tring[y & 511u]];
+#pragma unroll
+				for (int r = 0; r < R; ++r) eq[k][r] = sm.eq[c][lane][r];
+			}
+			uint32_t tops = 0x55555555u;                                   // stripe 0: +1 in every column
+			if (lane == 0 && stripe) {
+				const uint32_t w0 = group_bits((tb - 1u) >> 4) >> 30;              // column tb: last column of its group
+				tops = w0 | (group_bits(tb >> 4) << 2);                            // columns tb+1 .. tb+15
+			}
+			const bool first = lane == 0;
+			uint32_t packed = 0;
+#pragma unroll
+			for (int k = 0; k < 16; ++k) {
+				uint32_t hp = __shfl_up_sync(0xffffffffu, sP, 1), hn = __shfl_up_sync(0xffffffffu, sN, 1);
+				if (first) { hp = (tops >> (2 * k)) & 1u; hn = (tops >> (2 * k + 1)) & 1u; }
+				column(eq[k], hp, hn);
+				sP = hp; sN = hn;
+				packed |= (hp | (hn << 1)) << (2 * k);
+			}
+			if (lane == 31 && !last_stripe) st_relaxed_u64(bnd_out + ((tb - 32u) >> 4), tag_out | packed);
+			if (pf) { pf_word = nw; pf_group = ng; }
+		};
+
+		for (uint32_t tb = 0; tb <= t_last; tb += 16) {
+			if ((tb & 255u) == 32u && tb > 32u) {
+				const uint32_t c = (tb >> 8) + 1u;
+				__syncwarp();
+				if (c < n_tiles) ring_issue<false>(sm.rg, tbase16, nullptr, c, lane);
+			}
+			if ((tb & 255u) == 224u) {
+				const uint32_t c = (tb >> 8) + 1u;
+				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
+			}
+			if (tb >= 32u && tb + 15u <= l2) {
+				steps16(tb);
+			} else {
+#pragma unroll 1
+				for (uint32_t k = 0; k < 16; ++k) step(tb + k);
+			}
+		}
+		__syncwarp();
+
+		if (own_r >= 0) { a.score[p] = dist; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = ST_MID; }
 		__syncwarp();
 	}
 }

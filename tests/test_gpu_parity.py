@@ -323,3 +323,31 @@ def test_k2_edge_shapes(A, aligner, oracle_mod, mode):
         sites = np.array(ss + [0], dtype=np.int32); site_off = np.array(so, dtype=np.uint64)
     md = "fit" if mode == "fitjump" else mode
     check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites, site_off)
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"A", b"ACGTNRYK", b"ACGTNRYKM", b"ACDEFGHIKLMNPQRSTVWY"])
+def test_edit_unit_cost_bit_parallel(A, aligner, oracle_mod, monkeypatch, alphabet):
+    """`edit -u 1` runs the bit-parallel (Myers) kernel when the reads use at most 8 distinct bytes,
+    the cell-by-cell kernel otherwise; both must give the reference's distance.  Shapes cover one
+    block, partial blocks, 1 / 2 / 4 blocks per lane, several stripes, targets shorter than a
+    hand-off block, and target symbols that never occur in the reads."""
+    rng = random.Random(99 + len(alphabet))
+    shapes = [(1, 1), (1, 40), (40, 1), (31, 33), (32, 32), (33, 31), (100, 5), (5, 100), (1024, 900), (1025, 1100),
+              (2048, 2000), (2049, 70), (4096, 4096), (4097, 4200), (9000, 3000), (3000, 9000), (700, 17), (17, 700)]
+    q, t = [], []
+    for l1, l2 in shapes:
+        base = bytes(rng.choice(alphabet) for _ in range(max(l1, l2)))
+        s1 = bytes(c if rng.random() > 0.1 else rng.choice(alphabet) for c in base[:l1])
+        s2 = bytearray(c if rng.random() > 0.1 else rng.choice(alphabet) for c in base[:l2])
+        for k in range(0, l2, 37):
+            s2[k] = ord("#")                                   # a byte no read contains
+        q.append(s1); t.append(bytes(s2))
+    for _ in range(60):
+        l1, l2 = rng.randint(1, 300), rng.randint(1, 300)
+        q.append(bytes(rng.choice(alphabet) for _ in range(l1))); t.append(bytes(rng.choice(alphabet) for _ in range(l2)))
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    prm = dict(m=1, u=1, o=-5, e=-1, j=-10, jump=False)
+    check_batch_vs_port(A, aligner, oracle_mod, "edit", prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl)
+    monkeypatch.setenv("AT_NO_BITPAR", "1")
+    check_batch_vs_port(A, aligner, oracle_mod, "edit", prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl)
