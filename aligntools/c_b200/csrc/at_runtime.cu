@@ -718,7 +718,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		CU(h, cudaStreamSynchronize(st));
 	}
 	mark("plan+jobs");
-	if (max_bnd_elems && s.d_bnd.alloc(max_bnd_elems * (linear ? sizeof(int32_t) : sizeof(int4)) + 64) != cudaSuccess) { set_err(h, "stripe boundary slabs of %llu MB", (unsigned long long)((max_bnd_elems * (linear ? 4 : 16)) >> 20)); return AT_E_NOMEM; }
+	if (max_bnd_elems && s.d_bnd.alloc(max_bnd_elems * (linear ? sizeof(uint64_t) : sizeof(int4)) + 64) != cudaSuccess) { set_err(h, "stripe boundary slabs of %llu MB", (unsigned long long)((max_bnd_elems * (linear ? 8 : 16)) >> 20)); return AT_E_NOMEM; }
 	if (!max_bnd_elems) CU(h, s.d_bnd.alloc(64));
 	CU(h, s.d_prog.alloc(max_prog_words + 1));
 	{
@@ -897,7 +897,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 		const uint32_t nc = c.k1 - c.k0;
 		CU(h, cudaMemsetAsync(s.d_counter.p, 0, 64 * sizeof(uint32_t), st));
 		if (c.prog_words) CU(h, cudaMemsetAsync(s.d_prog.p, 0, c.prog_words * sizeof(uint32_t), st));
-		if (s.bits && c.bnd_elems) CU(h, cudaMemsetAsync(s.d_bnd.p, 0, c.bnd_elems * sizeof(int32_t), st));   // tagged hand-off words of at_wave_edit_bits
+		if (b->mode >= AT_OVERLAP && c.bnd_elems) CU(h, cudaMemsetAsync(s.d_bnd.p, 0, c.bnd_elems * sizeof(uint64_t), st));   // tagged hand-off words of the single-plane kernels
 		CU(h, cudaEventRecord(e_begin, st));
 		if (first) { CU(h, cudaEventRecord(e_first, st)); first = false; }
 		for (size_t li = 0; li < c.launches.size(); ++li) {

@@ -90,6 +90,18 @@ __device__ __forceinline__ uint32_t ld_progress(const uint32_t *p)
 	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
+// tagged hand-off words of the single-plane kernels: 64-bit accesses are single-copy atomic, so a word that
+// carries its own tag needs neither a fence on the producer's side nor a flag on the consumer's
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p)
+{
+	uint64_t v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
 __device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
 {
 	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -441,11 +453,13 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
 		const bool last_stripe = stripe + 1 == n_stripes;
 		const uint32_t slab = (l2 + 4u) & ~3u;
-		int *bnd_pair = (int *)a.bnd + a.bnd_off[p - a.pair_base];
-		int *bnd_out = bnd_pair + (size_t)(stripe & 1u) * slab;
-		const int *bnd_in = bnd_pair + (size_t)((stripe & 1u) ^ 1u) * slab;
-		const uint32_t *prog_in = a.prog + (stripe ? job - 1 : job);
-		uint32_t seen = 0;
+		// boundary hand-off without fences: one 64-bit word per column = (stripe + 1) << 32 | value; the consumer
+		// validates the tag of every word it loads (the slabs are zeroed by the host before each run)
+		uint64_t *bnd_pair = (uint64_t *)a.bnd + a.bnd_off[p - a.pair_base];
+		uint64_t *bnd_out = bnd_pair + (size_t)(stripe & 1u) * slab;
+		const uint64_t *bnd_in = bnd_pair + (size_t)((stripe & 1u) ^ 1u) * slab;
+		const uint64_t tag_out = (uint64_t)(stripe + 1u) << 32;
+		const uint32_t tag_in = stripe;                                   // the predecessor's (stripe - 1) + 1
 		const uint32_t row0 = stripe * RPP + lane * R;
 
 		__syncwarp();
@@ -468,10 +482,12 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
 		int capV = OV ? gap : 0, capJ = 0;                        // overlap: M[l1][0] = 0 seeds the search (:954-959)
 
-		int pre = 0;
+		uint64_t pre = 0;
 		if (stripe) {
-			wait_columns(prog_in, min(l2, 31u), seen, lane);
-			if ((uint32_t)lane <= l2) pre = __ldcg(bnd_in + lane);
+			// start lag: three hand-off blocks behind the predecessor, so that blocks requested one block ahead are valid on arrival
+			if (lane == 0) { const uint32_t c = min(l2, 96u); while ((uint32_t)(ld_relaxed_u64(bnd_in + c) >> 32) != tag_in) __nanosleep(200); }
+			__syncwarp();
+			if ((uint32_t)lane <= l2) pre = ld_relaxed_u64(bnd_in + lane);
 		}
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
 
@@ -526,17 +542,15 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 				__syncwarp();
 				if (!last_stripe && tb >= 64u) {
 					const int cidx = (int)tb - 63 + lane;
-					if (cidx >= 1 && cidx <= (int)l2) __stcg(bnd_out + cidx, sm.stage[(uint32_t)cidx & 63u]);
-					__syncwarp();
-					if (lane == 0) st_release(a.prog + job, min(tb - 32u, l2));
+					if (cidx >= 1 && cidx <= (int)l2) st_relaxed_u64(bnd_out + cidx, tag_out | (uint32_t)sm.stage[(uint32_t)cidx & 63u]);
 				}
 				if (stripe) {
-					sm.cring[(tb + lane) & 63u] = pre;
-					const uint32_t nxt = tb + 32u + lane;
-					if (tb + 32u <= l2) {
-						wait_columns(prog_in, min(l2, tb + 63u), seen, lane);
-						if (nxt <= l2) pre = __ldcg(bnd_in + nxt);
-					}
+					const uint32_t col = tb + lane;                       // `pre` was requested a block ago: make sure it is the predecessor's
+					if (col >= 1u && col <= l2)
+						while ((uint32_t)(pre >> 32) != tag_in) { __nanosleep(40); pre = ld_relaxed_u64(bnd_in + col); }
+					sm.cring[col & 63u] = (int)(uint32_t)pre;
+					const uint32_t nxt = col + 32u;
+					if (nxt <= l2) pre = ld_relaxed_u64(bnd_in + nxt);
 					__syncwarp();
 				}
 			}
@@ -566,9 +580,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 
 		if (!last_stripe) {
 			const int cidx = (int)t_last - 62 + lane;
-			if (cidx >= 1 && cidx <= (int)l2) __stcg(bnd_out + cidx, sm.stage[(uint32_t)cidx & 63u]);
-			__syncwarp();
-			if (lane == 0) st_release(a.prog + job, l2);
+			if (cidx >= 1 && cidx <= (int)l2) st_relaxed_u64(bnd_out + cidx, tag_out | (uint32_t)sm.stage[(uint32_t)cidx & 63u]);
 		} else if (cap_r >= 0) {
 			if (OV) { a.score[p] = (capV - gap) / S; a.end_i[p] = l1; a.end_j[p] = capJ; a.end_state[p] = ST_MID; }
 			else { a.score[p] = capV; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = ST_MID; }
@@ -597,17 +609,6 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 // membar per 32 columns -- 22 % of this kernel's stall samples when it was first written that way.)
 //   score = M[l1][l2] = l1 + sum over j of the horizontal difference at row l1.     SURVEY.md 8(f) #4.
 // =====================================================================================
-__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v)
-{
-	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p)
-{
-	uint64_t v;
-	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-	return v;
-}
-
 template <int R>
 __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const WaveArgs a)
 {
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 		const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
 		const bool last_stripe = stripe + 1 == n_stripes;
 		const uint32_t n_groups = (l2 + 15u) / 16u;                        // words per slab (the host reserves far more)
-		uint64_t *bnd_pair = (uint64_t *)((int *)a.bnd + a.bnd_off[p - a.pair_base]);
+		uint64_t *bnd_pair = (uint64_t *)a.bnd + a.bnd_off[p - a.pair_base];
 		uint64_t *bnd_out = bnd_pair + (size_t)(stripe & 1u) * n_groups;
 		const uint64_t *bnd_in = bnd_pair + (size_t)((stripe & 1u) ^ 1u) * n_groups;
 		const uint64_t tag_in = (uint64_t)stripe << 32;                    // the predecessor's tag: (stripe - 1) + 1
