@@ -72,28 +72,62 @@ struct TraceArgs {
 	uint32_t       *cigar;                // dense ops of the chunk
 	uint8_t        *aln1, *aln2;          // dense columns of the chunk
 	int             mode, jump;
+	int             lookahead;             // few, long walks (latency-bound): prefetch the pointer sectors ahead of the walker
 };
 
+// Cursor over a pair's pointer block (layout: at_kernels.cuh header).  The word of cell (i, j) is
+//   ptr[rowA(i) + ((j + lane(i)) >> SH) * RPP],   rowA(i) = stripe * G * RPP + lane * R + r,
+// with stripe / lane / r the position of row i-1 in the fill's geometry.  A traceback only ever moves
+// to row i-1, so rowA is kept incrementally (it just decrements, except across a stripe) instead of
+// being re-derived with two integer divisions per visited cell.
 struct PtrView {
 	const uint32_t *ptr, *ptrJ;
 	uint32_t R, RPP, G, GJ, half;
-	__device__ __forceinline__ uint32_t nib(uint32_t i, uint32_t j) const {
-		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
+	uint32_t r, lane;            // position of row i-1: row within the lane, lane within the stripe
+	size_t rowA, rowJ;           // word offsets of row i-1 in the nibble / 2-bit block and in the jump-bit plane
+	__device__ __forceinline__ void seek(uint32_t i) {            // i >= 1
+		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP;
+		lane = rem / R; r = rem - lane * R;
+		rowA = (size_t)stripe * G * RPP + (size_t)lane * R + r;
+		rowJ = (size_t)stripe * GJ * RPP + (size_t)lane * R + r;
+	}
+	__device__ __forceinline__ void up() {                        // row i-1 -> row i-2 (no-op bookkeeping when leaving row 0)
+		if (r) { --r; --rowA; --rowJ; return; }
+		r = R - 1;
+		if (lane) { --lane; --rowA; --rowJ; return; }
+		lane = 31;                                                // previous stripe: its last lane, last row
+		rowA = rowA - (size_t)G * RPP + (RPP - 1);
+		rowJ = rowJ - (size_t)GJ * RPP + (RPP - 1);
+	}
+	// Pull the sectors the walk will most likely need AHEAD steps from now into L2/L1: the path mostly runs
+	// along the diagonal (rows and columns both move back) or along a row (gap / jump runs).  A thread-serial
+	// pointer chase otherwise pays a full HBM round trip per new sector.
+	__device__ __forceinline__ void prefetch(uint32_t i, uint32_t j, int sh) const {
+		constexpr uint32_t AHEAD = 24;
+		if (i <= AHEAD + 1 || j <= AHEAD + 1 || rowA < AHEAD) return;
+		const uint32_t lane_then = lane - min(lane, (AHEAD + R - 1 - r) / R);               // rows per lane: R (approximate across a stripe edge)
+		const uint32_t *diag = ptr + (rowA - AHEAD) + (size_t)((j - AHEAD + lane_then) >> sh) * RPP;
+		const uint32_t *row = ptr + rowA + (size_t)((j - AHEAD + lane) >> sh) * RPP;
+		asm volatile("prefetch.global.L2 [%0];" :: "l"(diag));
+		asm volatile("prefetch.global.L2 [%0];" :: "l"(row));
+	}
+	__device__ __forceinline__ uint32_t nib(uint32_t j) const {
+		const uint32_t t = j + lane;
 		if (half) {   // packed s16x2: 4 steps x 2 pairs per word, single stripe
-			const uint32_t w = __ldg(ptr + ((size_t)(t >> 2) * 32 + lane) * R + r);
+			const uint32_t w = __ldg(ptr + rowA + (size_t)(t >> 2) * RPP);
 			return (w >> (16 * (half - 1) + 4 * (3 - (t & 3)))) & 15u;
 		}
-		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 3)) * 32 + lane) * R + r);
+		const uint32_t w = __ldg(ptr + rowA + (size_t)(t >> 3) * RPP);
 		return (w >> (4 * (7 - (t & 7)))) & 15u;
 	}
-	__device__ __forceinline__ uint32_t jbit(uint32_t i, uint32_t j) const {
-		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
-		const uint32_t w = __ldg(ptrJ + ((size_t)(stripe * GJ + (t >> 5)) * 32 + lane) * R + r);
+	__device__ __forceinline__ uint32_t jbit(uint32_t j) const {
+		const uint32_t t = j + lane;
+		const uint32_t w = __ldg(ptrJ + rowJ + (size_t)(t >> 5) * RPP);
 		return (w >> (31 - (t & 31))) & 1u;
 	}
-	__device__ __forceinline__ uint32_t two(uint32_t i, uint32_t j) const {   // overlap: 2 bits, 16 steps per word
-		const uint32_t ri = i - 1, stripe = ri / RPP, rem = ri - stripe * RPP, lane = rem / R, r = rem - lane * R, t = j + lane;
-		const uint32_t w = __ldg(ptr + ((size_t)(stripe * G + (t >> 4)) * 32 + lane) * R + r);
+	__device__ __forceinline__ uint32_t two(uint32_t j) const {   // overlap: 2 bits, 16 steps per word
+		const uint32_t t = j + lane;
+		const uint32_t w = __ldg(ptr + rowA + (size_t)(t >> 4) * RPP);
 		return (w >> (2 * (15 - (t & 15)))) & 3u;
 	}
 };
@@ -128,14 +162,16 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 	RunWriter w;
 	w.dst = a.scratch + a.scratch_off[k]; w.n_ops = w.n_cols = w.run = 0; w.op = 0;
 	uint32_t i = a.end_i[p], j = a.end_j[p], state = a.end_state[p];
+	if (i) pv.seek(i);
 
 	if (a.mode == MODE_OVERLAP) {
 		while (j > 0) {                                   // :899
 			if (i == 0) break;                            // row 0 is -inf (:937): unreachable on a finite path
-			const uint32_t c = pv.two(i, j);              // bit 1: RIGHT beat both; bit 0: DIAGONAL beat LEFT
-			if (c & 2u)      { --i; w.col(CIG_I); }                  // RIGHT
-			else if (c & 1u) { --i; --j; w.col(CIG_M); }             // DIAGONAL
-			else             { --j; w.col(CIG_D); }                  // LEFT
+			if (a.lookahead) pv.prefetch(i, j, 4);
+			const uint32_t c = pv.two(j);                 // bit 1: RIGHT beat both; bit 0: DIAGONAL beat LEFT
+			if (c & 2u)      { --i; pv.up(); w.col(CIG_I); }                  // RIGHT
+			else if (c & 1u) { --i; pv.up(); --j; w.col(CIG_M); }             // DIAGONAL
+			else             { --j; w.col(CIG_D); }                           // LEFT
 		}
 	} else {
 		bool home = false;
@@ -143,16 +179,17 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 			const bool go = a.mode == MODE_FIT ? (i > 0) : (i > 0 && j > 0);   // :562 | :377, :771
 			if (!go || home) break;
 			if (j == 0 && state != ST_LOW) break;         // only reachable with corrupt pointers: never index s2[-1]
-			const uint32_t nb = pv.nib(i, j);
-			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; w.col(CIG_I); }
+			if (a.lookahead) pv.prefetch(i, j, pv.half ? 2 : 3);
+			const uint32_t nb = pv.nib(j);
+			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; pv.up(); w.col(CIG_I); }
 			else if (state == ST_MID) {
 				const uint32_t pm = nb & 3u;
-				--i; --j; w.col(CIG_M);
+				--i; pv.up(); --j; w.col(CIG_M);
 				if (pm == 3 && a.mode == MODE_LOCAL) home = true;              // HOME: column emitted, then stop (:788-791)
 				else state = pm;
 			}
 			else if (state == ST_UPP) { state = (nb & 8u) ? ST_UPP : ST_MID; --j; w.col(CIG_D); }
-			else                      { state = pv.jbit(i, j) ? ST_JUMP : ST_MID; --j; w.col(CIG_N); }
+			else                      { state = pv.jbit(j) ? ST_JUMP : ST_MID; --j; w.col(CIG_N); }
 		}
 	}
 	a.beg_i[p] = i; a.beg_j[p] = j;

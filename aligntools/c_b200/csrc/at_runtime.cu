@@ -958,6 +958,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			ta.scratch = s.d_scratch.p; ta.scratch_off = c.d_scratch_off.p;
 			ta.cigar = nullptr; ta.aln1 = nullptr; ta.aln2 = nullptr;
 			ta.mode = b->mode; ta.jump = jump ? 1 : 0;
+			ta.lookahead = nc < 32768u ? 1 : 0;       // with many short walks the chase is throughput-bound and the prefetches only add traffic
 			if (s.workspace) at_traceback_walk<true><<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
 			else at_traceback_walk<false><<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
