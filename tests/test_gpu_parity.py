@@ -351,3 +351,42 @@ def test_edit_unit_cost_bit_parallel(A, aligner, oracle_mod, monkeypatch, alphab
     check_batch_vs_port(A, aligner, oracle_mod, "edit", prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl)
     monkeypatch.setenv("AT_NO_BITPAR", "1")
     check_batch_vs_port(A, aligner, oracle_mod, "edit", prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl)
+
+
+def test_config2_full_size_checksums(A, aligner):
+    """BASELINE config 2 at its full size (1 Mi pairs): a checksum of checksums against the run that was
+    compared with the oracle pair by pair (tests/golden/c2_full_checksums.json), through both the resident
+    and the pipelined one-shot path; plus size-independent properties of every alignment -- CIGAR column
+    counts consistent with the cells the traceback started and stopped in."""
+    import json
+    import os
+    from aligntools.c_b200 import synth
+    from helpers import GOLD
+    with open(os.path.join(GOLD, "c2_full_checksums.json")) as f:
+        gold = json.load(f)
+    w = synth.config2_local(n_pairs=gold["pairs"])
+    opt = A.Opt(**w["params"])
+    b = aligner.batch("local", opt, w["q"], w["q_off"], w["q_len"], w["t"], w["t_off"], w["t_len"], out_flags=A.OUT_CIGAR)
+    tm = b.run()
+    res = b.fetch()
+    b.free()
+    n = gold["pairs"]
+    assert tm.cells == gold["cells"]
+    assert int(res.score.astype(np.int64).sum()) == gold["score_sum"]
+    assert int(res.cigar_off[n]) == gold["cigar_ops"]
+    ops = res.cigar[:gold["cigar_ops"]]
+    runs = (ops >> 4).astype(np.int64)
+    code = ops & 3
+    assert int(runs.sum()) == gold["alignment_columns"]
+    # per pair: rows consumed = M + I columns = end_i - beg_i, target columns consumed = M + D = end_j - beg_j
+    starts = res.cigar_off[:n].astype(np.int64)
+    nonempty = res.cigar_off[1:n + 1] > res.cigar_off[:n]
+    rows = np.add.reduceat(np.where(code != 2, runs, 0), starts[nonempty])
+    cols = np.add.reduceat(np.where(code != 1, runs, 0), starts[nonempty])
+    assert np.array_equal(rows, (res.end_i.astype(np.int64) - res.beg_i)[nonempty])
+    assert np.array_equal(cols, (res.end_j.astype(np.int64) - res.beg_j)[nonempty])
+    assert np.all(res.score >= 0) and np.all(res.end_i <= 150) and np.all(res.end_j <= 500)
+    one = aligner.align_arrays("local", opt, w["q"], w["q_off"], w["q_len"], w["t"], w["t_off"], w["t_len"], out_flags=A.OUT_CIGAR,
+                               cigar_cap=gold["cigar_ops"] + 16)
+    assert np.array_equal(one.score, res.score) and np.array_equal(one.cigar_off, res.cigar_off)
+    assert np.array_equal(one.cigar[:gold["cigar_ops"]], ops)
