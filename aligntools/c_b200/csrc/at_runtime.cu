@@ -11,7 +11,7 @@
 #include "at_kernels.cuh"
 
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <atomic>
@@ -448,7 +448,8 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
 	// target alphabet of the shard -> query-profile variant of K1 (affine modes) when it has at most 4 symbols
 	s.prof = false; s.syms = 0;
-	if (b->mode <= AT_FIT && in->encoding == AT_SEQ_2BIT) {
+	const bool bits_wanted = b->mode == AT_EDIT && b->prm.u == 1 && !getenv("AT_NO_BITPAR");      // then symmap describes the reads instead
+	if (!bits_wanted && in->encoding == AT_SEQ_2BIT) {
 		uint8_t map[256]; memset(map, 0, sizeof map);
 		map['C'] = 1; map['G'] = 2; map['T'] = 3;
 		s.syms = (uint32_t)'A' | ((uint32_t)'C' << 8) | ((uint32_t)'G' << 16) | ((uint32_t)'T' << 24);
@@ -456,7 +457,7 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, st));
 		CU(h, cudaStreamSynchronize(st));
 		s.prof = !getenv("AT_NO_PROFILE");
-	} else if (b->mode <= AT_FIT && !getenv("AT_NO_PROFILE")) {
+	} else if (!bits_wanted && !getenv("AT_NO_PROFILE")) {
 		uint32_t set8[8];
 		CU(h, s.d_symset.alloc(8));
 		CU(h, cudaMemsetAsync(s.d_symset.p, 0, 8 * sizeof(uint32_t), st));
@@ -848,23 +849,23 @@ template <bool PROF> static fill2_fn affine_kernel_r(int kind, int R)
 	}
 }
 static fill2_fn affine_kernel(int kind, int R, bool prof) { return prof ? affine_kernel_r<true>(kind, R) : affine_kernel_r<false>(kind, R); }
-template <int MODE> static wave_fn wave_linear_fn(int R)
+template <int MODE, bool PROF> static wave_fn wave_linear_fn(int R)
 {
 	switch (R) {
-	case 1: return at_wave_linear<MODE, 1>; case 2: return at_wave_linear<MODE, 2>; case 3: return at_wave_linear<MODE, 3>;
-	case 4: return at_wave_linear<MODE, 4>; case 5: return at_wave_linear<MODE, 5>; case 6: return at_wave_linear<MODE, 6>;
-	case 7: return at_wave_linear<MODE, 7>; default: return at_wave_linear<MODE, 8>;
+	case 1: return at_wave_linear<MODE, 1, PROF>; case 2: return at_wave_linear<MODE, 2, PROF>; case 3: return at_wave_linear<MODE, 3, PROF>;
+	case 4: return at_wave_linear<MODE, 4, PROF>; case 5: return at_wave_linear<MODE, 5, PROF>; case 6: return at_wave_linear<MODE, 6, PROF>;
+	case 7: return at_wave_linear<MODE, 7, PROF>; default: return at_wave_linear<MODE, 8, PROF>;
 	}
 }
 static wave_fn bits_kernel(int R) { return R == 1 ? at_wave_edit_bits<1> : (R == 2 ? at_wave_edit_bits<2> : at_wave_edit_bits<4>); }
-static wave_fn wave_kernel(int mode, bool jump, int R)
+static wave_fn wave_kernel(int mode, bool jump, int R, bool prof)
 {
 	switch (mode) {
 	case AT_GLOBAL: return at_wave_affine<MODE_GLOBAL, false>;
 	case AT_LOCAL: return at_wave_affine<MODE_LOCAL, false>;
 	case AT_FIT: return jump ? at_wave_affine<MODE_FIT, true> : at_wave_affine<MODE_FIT, false>;
-	case AT_OVERLAP: return wave_linear_fn<MODE_OVERLAP>(R);
-	default: return wave_linear_fn<MODE_EDIT>(R);
+	case AT_OVERLAP: return prof ? wave_linear_fn<MODE_OVERLAP, true>(R) : wave_linear_fn<MODE_OVERLAP, false>(R);
+	default: return prof ? wave_linear_fn<MODE_EDIT, true>(R) : wave_linear_fn<MODE_EDIT, false>(R);
 	}
 }
 
@@ -902,7 +903,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 		if (first) { CU(h, cudaEventRecord(e_first, st)); first = false; }
 		for (size_t li = 0; li < c.launches.size(); ++li) {
 			Launch &l = c.launches[li];
-			const void *fn = l.kind == LK_BITS ? (const void *)bits_kernel(l.r) : l.kind == LK_WAVE ? (const void *)wave_kernel(b->mode, jump, l.r)
+			const void *fn = l.kind == LK_BITS ? (const void *)bits_kernel(l.r) : l.kind == LK_WAVE ? (const void *)wave_kernel(b->mode, jump, l.r, s.prof)
 			                                   : (const void *)affine_kernel(l.kind == LK_PACKED ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode), l.r, s.prof);
 			const int warps = l.kind >= LK_WAVE ? AT_WAVE_WARPS : AT_FILL_WARPS;
 			const size_t dyn_smem = l.kind >= LK_WAVE ? 0 : fill_smem_bytes(l.r, l.kind == LK_PACKED, s.prof);
@@ -916,7 +917,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			if (dom) CU(h, cudaEventRecord(s.evk[0], st));
 			if (l.kind >= LK_WAVE) {
 				WaveArgs wa;
-				wa.symmap = s.d_symmap.p;
+				wa.symmap = s.d_symmap.p; wa.syms = s.syms;
 				wa.q = s.d_q.p; wa.q_off = s.d_q_off.p; wa.q_len = s.d_q_len.p;
 				wa.t = s.d_t.p; wa.t_off = s.d_t_off.p; wa.t_len = s.d_t_len.p;
 				wa.jmask = s.d_jmask.p; wa.tasks = l.d_tasks.p; wa.n_tasks = (uint32_t)l.h_tasks.size();
@@ -970,8 +971,8 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				s.launches++;
 			} else {
 				size_t tmp_bytes = 0;
-				cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_ops(s.d_n_ops.p + c.k0, CastU64());
-				cub::TransformInputIterator<uint64_t, CastU64, const uint32_t *> it_cols(s.d_n_cols.p + c.k0, CastU64());
+				auto it_ops = thrust::make_transform_iterator((const uint32_t *)(s.d_n_ops.p + c.k0), CastU64());
+				auto it_cols = thrust::make_transform_iterator((const uint32_t *)(s.d_n_cols.p + c.k0), CastU64());
 				CU(h, cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
 				CU(h, s.d_scan_tmp.alloc(tmp_bytes + 16));
 				CU(h, cudaMemsetAsync(c.d_ops_off.p, 0, sizeof(uint64_t), st));

@@ -51,7 +51,9 @@ struct WaveArgs {
 	int32_t        *score;   uint32_t *end_i;  uint32_t *end_j;  uint8_t *end_state;
 	int             m, u, o, e, jp;
 	int             want_ptr;
-	const uint8_t  *symmap;  // at_wave_edit_bits: byte -> code 0..7 of the shard's READ alphabet, 8 = not in it
+	const uint8_t  *symmap;  // at_wave_edit_bits: byte -> code 0..7 of the shard's READ alphabet, 8 = not in it;
+	                         // at_wave_linear<.., PROF>: byte -> code 0..3 of the shard's TARGET alphabet
+	uint32_t        syms;    // PROF: the byte of code c in bits 8c..8c+7
 };
 
 // ---- TMA (bulk async copy) + mbarrier + release/acquire helpers ----
@@ -412,18 +414,25 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 // pointer is two difference flags: bit 0 = diagonal beat left, bit 1 = up beat both
 // (reference order LEFT, DIAGONAL, RIGHT with first-strictly-greater ties, :944-947).
 // =====================================================================================
-template <int MODE, int R>
+// PROF (targets of the shard use at most four distinct bytes): the substitution term comes from a per-warp
+// query profile in shared memory, prof[code][lane][r] = 0 on a match, -+penalty otherwise, as in K1 -- one
+// 64-bit LDS per two rows and an add instead of xor / min / multiply-add per cell (the ALU pipe is this
+// kernel's limiter); a.symmap maps target bytes to codes.
+template <int MODE, int R, bool PROF>
 __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveArgs a)
 {
 	constexpr int RPP = 32 * R;
 	constexpr bool OV = MODE == MODE_OVERLAP;
 	constexpr int UNR = OV ? AT_WAVE_UNROLL_OVERLAP : AT_WAVE_UNROLL_EDIT;
-	struct __align__(16) Smem { WaveRing<false> rg; int cring[64]; int stage[64]; };
+	constexpr int LS = prof_lane_stride(R);
+	struct __align__(16) Smem { int prof[PROF ? 4 : 1][PROF ? 32 : 1][PROF ? LS : 2]; WaveRing<false> rg; int cring[64]; int stage[64]; };
 	__shared__ Smem sm_all[AT_WAVE_WARPS];
+	__shared__ uint8_t symmap_s[PROF ? 256 : 16];
 	Smem &sm = sm_all[threadIdx.x >> 5];
 	const int lane = threadIdx.x & 31;
+	if (PROF) { for (int x = threadIdx.x; x < 256; x += blockDim.x) symmap_s[x] = a.symmap[x]; }
 	if (lane == 0) { mbar_init(&sm.rg.bar[0], 1); mbar_init(&sm.rg.bar[1], 1); fence_proxy_async_smem(); }
-	__syncwarp();
+	__syncthreads();
 	uint32_t ring_par = 0;
 
 	// overlap: S = 4, step cost o, substitution m / u; edit: S = 1, step cost +1, substitution 0 / u
@@ -475,7 +484,13 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 			ac[r] = ri < l1 ? ((uint32_t)q[ri] << 16) : 0x4u;
 			Vl[r] = OV ? gap : (int)ri + 1;
 			acc[r] = 0;
+			if (PROF) {
+				const uint32_t qa = ri < l1 ? (uint32_t)q[ri] : 0x100u;
+#pragma unroll
+				for (int c = 0; c < 4; ++c) sm.prof[c][lane][r] = qa == ((a.syms >> (8 * c)) & 255u) ? 0 : (int)pen * nsg;
+			}
 		}
+		if (PROF) __syncwarp();
 		int sV = Vl[R - 1];
 		int pD = 0;                                               // diagonal input of the lane's first row (set at the step with j = 0)
 		const int col0 = OV ? gap : (int)row0;                    // V(row0, 0): the row above this lane's strip
@@ -503,12 +518,19 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 			pD = rV + dm;
 			if (!checked || (j >= 1 && j <= (int)l2)) {
 				const uint32_t y = (uint32_t)(j - 1) + sh;
-				const uint32_t c = (uint32_t)sm.rg.tring[y & 511u] << 16;
+				const uint32_t c = PROF ? (uint32_t)symmap_s[sm.rg.tring[y & 511u]] : (uint32_t)sm.rg.tring[y & 511u] << 16;
+				int pw[LS];                                                       // PROF: substitution terms of this lane's rows
+				if (PROF) {
+					const int2 *pp = (const int2 *)&sm.prof[c][lane][0];
+#pragma unroll
+					for (int r2 = 0; r2 < (R + 1) / 2; ++r2) { const int2 v2 = pp[r2]; pw[2 * r2] = v2.x; pw[2 * r2 + 1] = v2.y; }
+				}
 				int Vup = rV, v = 0;
 #pragma unroll
 				for (int r = 0; r < R; ++r) {
-					const int tt = (int)min(ac[r] ^ c, pen);                      // 0 on a match
-					const int diag = tt * nsg + D;
+					int diag;
+					if (PROF) diag = D + pw[r];
+					else { const int tt = (int)min(ac[r] ^ c, pen); diag = tt * nsg + D; }   // tt: 0 on a match
 					D = Vl[r] + dm;
 					if (OV) {
 						const int v1 = max(Vl[r], diag);                          // LEFT keeps ties (:944)
