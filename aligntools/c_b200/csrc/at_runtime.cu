@@ -861,9 +861,10 @@ static wave_fn bits_kernel(int R) { return R == 1 ? at_wave_edit_bits<1> : (R ==
 static wave_fn wave_kernel(int mode, bool jump, int R, bool prof)
 {
 	switch (mode) {
-	case AT_GLOBAL: return at_wave_affine<MODE_GLOBAL, false>;
-	case AT_LOCAL: return at_wave_affine<MODE_LOCAL, false>;
-	case AT_FIT: return jump ? at_wave_affine<MODE_FIT, true> : at_wave_affine<MODE_FIT, false>;
+	case AT_GLOBAL: return prof ? at_wave_affine<MODE_GLOBAL, false, true> : at_wave_affine<MODE_GLOBAL, false, false>;
+	case AT_LOCAL: return prof ? at_wave_affine<MODE_LOCAL, false, true> : at_wave_affine<MODE_LOCAL, false, false>;
+	case AT_FIT: return jump ? (prof ? at_wave_affine<MODE_FIT, true, true> : at_wave_affine<MODE_FIT, true, false>)
+	                         : (prof ? at_wave_affine<MODE_FIT, false, true> : at_wave_affine<MODE_FIT, false, false>);
 	case AT_OVERLAP: return prof ? wave_linear_fn<MODE_OVERLAP, true>(R) : wave_linear_fn<MODE_OVERLAP, false>(R);
 	default: return prof ? wave_linear_fn<MODE_EDIT, true>(R) : wave_linear_fn<MODE_EDIT, false>(R);
 	}

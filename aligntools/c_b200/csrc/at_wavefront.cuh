@@ -146,20 +146,25 @@ __device__ __forceinline__ void wait_columns(const uint32_t *prog, uint32_t need
 // =====================================================================================
 // Affine kernel: global / local / fit (+jump), int32 lanes, R = 8 rows per lane.
 // =====================================================================================
-template <int MODE, bool JUMP>
+// PROF (targets of the shard use at most four distinct bytes): query profile in shared memory as in K1,
+// prof[code][lane][r] = 8 * s(read row, target symbol); the carried H then holds H, not H + m.
+template <int MODE, bool JUMP, bool PROF>
 __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveArgs a)
 {
 	constexpr int R = 8, RPP = 32 * R;
-	struct __align__(16) Smem { WaveRing<JUMP> rg; int4 cring[64]; int4 stage[64]; };
+	constexpr int LS = prof_lane_stride(R);
+	struct __align__(16) Smem { int prof[PROF ? 4 : 1][PROF ? 32 : 1][PROF ? LS : 2]; WaveRing<JUMP> rg; int4 cring[64]; int4 stage[64]; };
 	__shared__ Smem sm_all[AT_WAVE_WARPS];
+	__shared__ uint8_t symmap_s[PROF ? 256 : 16];
 	Smem &sm = sm_all[threadIdx.x >> 5];
 	const int lane = threadIdx.x & 31;
+	if (PROF) { for (int x = threadIdx.x; x < 256; x += blockDim.x) symmap_s[x] = a.symmap[x]; }
 	if (lane == 0) { mbar_init(&sm.rg.bar[0], 1); mbar_init(&sm.rg.bar[1], 1); fence_proxy_async_smem(); }
-	__syncwarp();
+	__syncthreads();
 	uint32_t ring_par = 0;      // bit s: parity of the next completion of slot s's mbarrier
 
 	const int m = a.m, u = a.u, o = a.o, e = a.e;
-	const int m8 = 8 * m, o8 = 8 * o, e8 = 8 * e;
+	const int m8 = PROF ? 0 : 8 * m, o8 = 8 * o, e8 = 8 * e;      // m8: what the carried H holds on top of H (H + m in the xor/min variant)
 	const uint32_t mu8 = (uint32_t)(8 * (m >= u ? m - u : u - m));
 	const int nsg = m >= u ? -1 : 1;
 	const int ZERO = 0, NEGV = AT_NEG;
@@ -205,12 +210,18 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 			const uint32_t ri = row0 + r;
 			const int i = (int)ri + 1;
 			ac[r] = ri < l1 ? ((uint32_t)q[ri] << 16) : 0x4u;
+			if (PROF) {
+				const uint32_t qa = ri < l1 ? (uint32_t)q[ri] : 0x100u;
+#pragma unroll
+				for (int c = 0; c < 4; ++c) sm.prof[c][lane][r] = 8 * (qa == ((a.syms >> (8 * c)) & 255u) ? m : u);
+			}
 			crow[r] = ri < l1 ? 7 - r : -(1 << 28);
 			if (MODE == MODE_GLOBAL)     { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = 8 * (o + e * i) + m8; Cl[r] = ST_LOW; }      // :432-436
 			else if (MODE == MODE_LOCAL) { Mol[r] = ZERO + o8; Ul[r] = ZERO; Hl[r] = ZERO + m8; Cl[r] = ST_LOW; }           // calloc zeros
 			else                         { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = NEGV; Cl[r] = ST_MID; }                     // :612-617
 			Jl[r] = NEGV; acc[r] = 0; accJ[r] = 0;
 		}
+		if (PROF) __syncwarp();
 		int sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
 		int sL = MODE == MODE_GLOBAL ? 8 * (o + e * (int)(row0 + R)) : (MODE == MODE_LOCAL ? ZERO : NEGV);
 		int pH, pC;      // H(row0, 0) + m and its code: the row above this lane's strip, column 0
@@ -257,15 +268,22 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 			pH = rH; pC = rC;
 			if (!checked || (j >= 1 && j <= (int)l2)) {
 				const uint32_t y = (uint32_t)(j - 1) + sh;
-				const uint32_t c = (uint32_t)sm.rg.tring[y & 511u] << 16;
+				const uint32_t c = PROF ? (uint32_t)symmap_s[sm.rg.tring[y & 511u]] : (uint32_t)sm.rg.tring[y & 511u] << 16;
+				int pw[LS];                                                       // PROF: 8 * s of this lane's rows against the column's symbol
+				if (PROF) {
+					const int2 *pp = (const int2 *)&sm.prof[c][lane][0];
+#pragma unroll
+					for (int r2 = 0; r2 < R / 2; ++r2) { const int2 v2 = pp[r2]; pw[2 * r2] = v2.x; pw[2 * r2 + 1] = v2.y; }
+				}
 				int jadd = 0;
 				if (JUMP) jadd = sm.rg.jring[y & 511u] ? AT_NEG : 8 * (a.jp - o);     // M[i][j-1] + jump, or barred (:659-665)
 				int Lup = rL, MoUp = rM, Mo = 0, Ln = 0, Hm = 0, code = 0;
 				const int kold = kbest;
 #pragma unroll
 				for (int r = 0; r < R; ++r) {
-					const int tt = (int)min(ac[r] ^ c, mu8);                      // 0 on a match, 8|m-u| otherwise
-					const int Mraw = tt * nsg + D;                                // H(i-1,j-1) + s
+					int Mraw;                                                     // H(i-1,j-1) + s
+					if (PROF) Mraw = D + pw[r];
+					else { const int tt = (int)min(ac[r] ^ c, mu8); Mraw = tt * nsg + D; }   // tt: 0 on a match, 8|m-u| otherwise
 					int Mn = Mraw, pm = DC;
 					if (MODE == MODE_LOCAL) { Mn = max(Mraw, ZERO); pm = DC | (int)min((uint32_t)(Mn - Mraw), 3u); }   // HOME (:825)
 					const int Lext = Lup + e8;
