@@ -677,7 +677,6 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 		const uint32_t sh = (uint32_t)((uintptr_t)tbase & 15u);
 		const uint8_t *tbase16 = tbase - sh;
 		const uint32_t n_tiles = (l2 + sh + 255u) >> 8;
-		const uint32_t t_last = (l2 + 31u) | 31u;
 		const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
 		const bool last_stripe = stripe + 1 == n_stripes;
 		const uint32_t n_groups = (l2 + 15u) / 16u;                        // words per slab (the host reserves far more)
@@ -735,7 +734,11 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 		}
 		__syncwarp();
 
-		uint32_t sP = 0, sN = 0;       // hp / hn leaving the lane's last block (last computed column)
+		// Lane k works on column j = t - 2k - 1: a skew of TWO steps per lane.  What lane k-1 produces at step t
+		// is needed by lane k only at step t+2, so the shuffle that carries it (about 28 cycles) is off the
+		// critical path -- the chain per step is the column update alone.  inA / inB: the neighbour's outputs
+		// received at the end of the previous two steps (inA is the one due now).
+		uint32_t sP = 0, sN = 0, inA_p = 0, inA_n = 0, inB_p = 0, inB_n = 0;
 		// one column of the lane's R blocks; eq[] = match vectors of the column's symbol, (hp, hn) = horizontal
 		// difference entering the first block, replaced by the one leaving the last block
 		auto column = [&](const uint32_t (&eq)[R], uint32_t &hp, uint32_t &hn) {
@@ -756,10 +759,14 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 				hp = op; hn = on;
 			}
 		};
+		auto pass_on = [&]() {                                             // end of a step: send this step's output down, age the queue
+			inA_p = inB_p; inA_n = inB_n;
+			inB_p = __shfl_up_sync(0xffffffffu, sP, 1); inB_n = __shfl_up_sync(0xffffffffu, sN, 1);
+		};
 		auto step = [&](const uint32_t t) {                                // any step: range-checked
-			const int j = (int)t - lane;
+			const int j = (int)t - 2 * lane - 1;
 			const bool on = j >= 1 && j <= (int)l2;
-			uint32_t hp = __shfl_up_sync(0xffffffffu, sP, 1), hn = __shfl_up_sync(0xffffffffu, sN, 1);
+			uint32_t hp = inA_p, hn = inA_n;
 			if (lane == 0 && on) {
 				if (stripe == 0) { hp = 1; hn = 0; }                               // M[0][j] - M[0][j-1] = 1 (:302)
 				else { const uint32_t w = group_bits(((uint32_t)j - 1u) >> 4) >> (2u * (((uint32_t)j - 1u) & 15u)); hp = w & 1u; hn = (w >> 1) & 1u; }
@@ -777,12 +784,12 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 					if ((((uint32_t)j - 1u) & 15u) == 15u || j == (int)l2) { st_relaxed_u64(bnd_out + (((uint32_t)j - 1u) >> 4), tag_out | out_bits); out_bits = 0; }
 				}
 			}
+			pass_on();
 		};
-		// 16 in-range steps (tb a multiple of 16, every lane inside the matrix).  Everything that is not on
-		// the serial chain -- shuffle, half a dozen dependent logic ops, next shuffle -- is done up front:
-		// the shared-memory reads, and lane 0's sixteen boundary inputs (column tb is the last one of the
-		// group in hand, tb+1 .. tb+15 open the next group).  Lane 31's columns tb-31 .. tb-16 are exactly one
-		// group: one 64-bit store, no fence.
+		// 16 in-range steps (tb a multiple of 16, every lane inside the matrix: tb >= 64, tb + 14 <= l2).
+		// Everything that is not on the serial chain is done up front: the shared-memory reads, and lane 0's
+		// sixteen boundary inputs (columns tb-1, tb close the group in hand, tb+1 .. tb+14 open the next).
+		// Lane 31's columns tb-63 .. tb-48 are exactly one group: one 64-bit store, no fence.
 		auto steps16 = [&](const uint32_t tb) {
 			uint64_t nw = 0;                                               // lane 0 requests the NEXT call's group now
 			const uint32_t ng = (tb >> 4) + 1u;
@@ -791,41 +798,43 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 			uint32_t eq[16][R];
 #pragma unroll
 			for (int k = 0; k < 16; ++k) {
-				const uint32_t y = (uint32_t)((int)(tb + k) - lane - 1) + sh;
+				const uint32_t y = (uint32_t)((int)(tb + k) - 2 * lane - 2) + sh;
 				const uint32_t c = symmap_s[sm.rg.tring[y & 511u]];
 #pragma unroll
 				for (int r = 0; r < R; ++r) eq[k][r] = sm.eq[c][lane][r];
 			}
 			uint32_t tops = 0x55555555u;                                   // stripe 0: +1 in every column
 			if (lane == 0 && stripe) {
-				const uint32_t w0 = group_bits((tb - 1u) >> 4) >> 30;              // column tb: last column of its group
-				tops = w0 | (group_bits(tb >> 4) << 2);                            // columns tb+1 .. tb+15
+				const uint32_t w0 = group_bits((tb - 2u) >> 4) >> 28;              // columns tb-1, tb: the last two of their group
+				tops = w0 | (group_bits(tb >> 4) << 4);                            // columns tb+1 .. tb+14
 			}
 			const bool first = lane == 0;
 			uint32_t packed = 0;
 #pragma unroll
 			for (int k = 0; k < 16; ++k) {
-				uint32_t hp = __shfl_up_sync(0xffffffffu, sP, 1), hn = __shfl_up_sync(0xffffffffu, sN, 1);
+				uint32_t hp = inA_p, hn = inA_n;
 				if (first) { hp = (tops >> (2 * k)) & 1u; hn = (tops >> (2 * k + 1)) & 1u; }
 				column(eq[k], hp, hn);
 				sP = hp; sN = hn;
 				packed |= (hp | (hn << 1)) << (2 * k);
+				pass_on();
 			}
-			if (lane == 31 && !last_stripe) st_relaxed_u64(bnd_out + ((tb - 32u) >> 4), tag_out | packed);
+			if (lane == 31 && !last_stripe) st_relaxed_u64(bnd_out + ((tb - 64u) >> 4), tag_out | packed);
 			if (pf) { pf_word = nw; pf_group = ng; }
 		};
 
-		for (uint32_t tb = 0; tb <= t_last; tb += 16) {
-			if ((tb & 255u) == 32u && tb > 32u) {
+		const uint32_t t_end = (l2 + 63u) | 15u;                           // lane 31 reaches column l2 at step l2 + 63
+		for (uint32_t tb = 0; tb <= t_end; tb += 16) {
+			if ((tb & 255u) == 96u && tb > 96u) {                          // lane 31 has left tile tb/256 - 1: refill its slot two tiles ahead
 				const uint32_t c = (tb >> 8) + 1u;
 				__syncwarp();
 				if (c < n_tiles) ring_issue<false>(sm.rg, tbase16, nullptr, c, lane);
 			}
-			if ((tb & 255u) == 224u) {
+			if ((tb & 255u) == 224u) {                                     // lane 0 enters tile tb/256 + 1 within the next 32 steps
 				const uint32_t c = (tb >> 8) + 1u;
 				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
 			}
-			if (tb >= 32u && tb + 15u <= l2) {
+			if (tb >= 64u && tb + 14u <= l2) {
 				steps16(tb);
 			} else {
 #pragma unroll 1
