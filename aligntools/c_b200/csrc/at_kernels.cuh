@@ -1,15 +1,20 @@
 // at_kernels.cuh -- sm_100a device code of the alignTools DP core.
 //
-// K1  at_fill_affine<MODE,R,JUMP,PACKED> : Gotoh M/L/U(/J) fill of short pairs (l1 <= 256), one pair
-//                                    (or two, packed s16x2) per warp          (at_fill_affine.cuh)
-// K2  at_wave_affine<MODE,JUMP>    : the same recurrences for long pairs: stripes of 256 rows
-//     at_wave_linear<MODE,R>         pipelined over warps / CTAs, TMA-staged target tiles; the
+// K1  at_fill_affine<MODE,R,JUMP,PACKED,PROF> : Gotoh M/L/U(/J) fill of short pairs (l1 <= 256), one pair
+//                                    (or two, packed s16x2) per warp; PROF = query profile in shared
+//                                    memory for targets of <= 4 distinct bytes   (at_fill_affine.cuh)
+// K2  at_wave_affine<MODE,JUMP,PROF> : the same recurrences for long pairs: stripes of 256 rows
+//     at_wave_linear<MODE,R,PROF>    pipelined over warps / CTAs, TMA-staged target tiles; the
 //                                    single-plane kernel (overlap max-plus / edit min-plus) serves
-//                                    every length                               (at_wavefront.cuh)
+//                                    every length;
+//     at_wave_edit_bits<R>         : bit-parallel (Myers) unit-cost edit distance in the same stripe
+//                                    pipeline                                   (at_wavefront.cuh)
 // K3  at_traceback_walk            : device traceback, one thread per pair chases the pointers
 //                                    once and leaves the reversed run-length ops in scratch;
 //     at_traceback_emit            : one warp per pair writes the dense CIGAR and replays it over
 //                                    the sequences into the gapped strings r1 / r2.
+// helpers: at_scan_offsets (offsets of the dense outputs), at_symbol_set (which bytes occur: picks the
+//     PROF / bit-parallel variants), at_build_jmask (jump blacklist), at_unpack_2bit (at_runtime.cu).
 //
 // Geometry.  Rows i <-> read s1, columns j <-> target s2.  A warp
 // sweeps a STRIPE of 32*R rows over all columns as a systolic array: lane k owns rows
