@@ -44,11 +44,14 @@ namespace at {
 
 // query-profile geometry: words per lane (>= R, even, half of it odd: conflict-free 64-bit loads)
 __host__ __device__ constexpr int prof_lane_stride(int R) { return R <= 2 ? 2 : (R <= 6 ? 6 : 10); }
+// K1 only: an odd R keeps its rows unpadded and reads them with 32-bit loads (an odd lane stride is
+// conflict-free too); the smaller table lets a fifth CTA fit an SM for R = 5
+__host__ __device__ constexpr int k1_lane_stride(int R) { return (R & 1) ? R : prof_lane_stride(R); }
 __host__ __device__ constexpr int prof_combs(bool packed) { return packed ? 16 : 4; }
 // dynamic shared memory of one CTA of at_fill_affine<.., R, .., PACKED, PROF>
 __host__ __device__ constexpr size_t fill_smem_bytes(int R, bool packed, bool prof)
 {
-	return (size_t)AT_FILL_WARPS * (prof ? (size_t)AT_RING * 2 + (size_t)prof_combs(packed) * 32 * prof_lane_stride(R) * 4
+	return (size_t)AT_FILL_WARPS * (prof ? (size_t)AT_RING * 2 + (size_t)prof_combs(packed) * 32 * k1_lane_stride(R) * 4
 	                                     : (size_t)AT_RING * 4);
 }
 
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 	static_assert(!PACKED || (MODE == MODE_LOCAL && !JUMP), "packed lanes: local mode");
 	constexpr uint32_t SPW = V::STEPS_PER_WORD;
 	constexpr int RPP = 32 * R;
-	constexpr int LS = prof_lane_stride(R), NC = prof_combs(PACKED);
+	constexpr int LS = k1_lane_stride(R), NC = prof_combs(PACKED);
 	constexpr uint32_t COMB_BYTES = 32u * LS * 4u;             // one comb's slice of the profile
 	constexpr size_t WARP_BYTES = fill_smem_bytes(R, PACKED, PROF) / AT_FILL_WARPS;
 
@@ -263,11 +266,17 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					uint32_t c = PROF ? (uint32_t)ring16[(uint32_t)(j - 1) & (AT_RING - 1)] : ring[(uint32_t)(j - 1) & (AT_RING - 1)];
 					T jadd = 0;
 					if (JUMP) { jadd = (c & 1u) ? (T)AT_NEG : V::delta(a.jp - o); c &= ~1u; }   // M[i][j-1] + jump, or barred (:659-665)
-					uint32_t pw[LS];                                // PROF: the profile words of this lane's rows for the column's comb
+					uint32_t pw[LS + 1];                            // PROF: the profile words of this lane's rows for the column's comb
 					if (PROF) {
-						const uint2 *pp = (const uint2 *)(prof_lane + c);
+						if (LS & 1) {
+							const uint32_t *pp = (const uint32_t *)(prof_lane + c);
 #pragma unroll
-						for (int r2 = 0; r2 < (R + 1) / 2; ++r2) { const uint2 v2 = pp[r2]; pw[2 * r2] = v2.x; pw[2 * r2 + 1] = v2.y; }
+							for (int r2 = 0; r2 < R; ++r2) pw[r2] = pp[r2];
+						} else {
+							const uint2 *pp = (const uint2 *)(prof_lane + c);
+#pragma unroll
+							for (int r2 = 0; r2 < (R + 1) / 2; ++r2) { const uint2 v2 = pp[r2]; pw[2 * r2] = v2.x; pw[2 * r2 + 1] = v2.y; }
+						}
 					}
 					T Lup = rL, MoUp = rM, Mo = 0, Ln = 0, Hm = 0, code = 0;
 					const T kold = kbest;
