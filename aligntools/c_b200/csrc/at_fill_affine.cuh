@@ -62,6 +62,7 @@ template <> struct Lanes<false> {
 	static constexpr int CSHIFT = 16;
 	static constexpr uint32_t STEPS_PER_WORD = 8;
 	__device__ __forceinline__ static T vmax(T a, T b) { return max(a, b); }
+	__device__ __forceinline__ static T vmax3(T a, T b, T c) { return __vimax3_s32(a, b, c); }
 	__device__ __forceinline__ static T flag(T d, uint32_t k) { return (T)min((uint32_t)d, k); }     // d >= 0
 	__device__ __forceinline__ static T addmax(T a, T b, T c) { return __viaddmax_s32(a, b, c); }
 	__device__ __forceinline__ static T delta(int v) { return 8 * v; }
@@ -75,6 +76,7 @@ template <> struct Lanes<true> {
 	static constexpr int CSHIFT = 8;
 	static constexpr uint32_t STEPS_PER_WORD = 4;
 	__device__ __forceinline__ static T vmax(T a, T b) { return __vmaxu2(a, b); }
+	__device__ __forceinline__ static T vmax3(T a, T b, T c) { return __vimax3_u16x2(a, b, c); }
 	__device__ __forceinline__ static T flag(T d, uint32_t k) { return __vminu2(d, k * 0x10001u); }
 	__device__ __forceinline__ static T addmax(T a, T b, T c) { return __viaddmax_u16x2(a, b, c); }
 	__device__ __forceinline__ static T delta(int v) { return (uint32_t)(8 * v * 0x10001); }           // exact 32-bit sum of both halves: for IADD/IMAD
@@ -299,9 +301,10 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 							fJ = V::flag(Jn - ent, 1);                          // stay in J only when strictly better (:660)
 						}
 						Mo = Mn + o8;
-						const T t1 = V::vmax(Ln, Mn);
-						T H = V::vmax(t1, Un);
-						code = V::flag(H - Ln, 1) + V::flag(H - t1, 1);         // 0 LOW, 1 MID, 2 UPP: first strictly greater, order L,M,U
+						T H = V::vmax3(Ln, Mn, Un);
+						// 0 LOW, 1 MID, 2 UPP: first strictly greater in the order L, M, U.  notL / notM are 0 or 3:
+						// L wins -> 0;  M wins (H > L, H == M) -> 3 & 1;  U wins (H > L, H > M) -> 3 & 2
+						code = V::flag(H - Ln, 3) & (V::flag(H - Mn, 3) ^ V::raw(1));
 						if (JUMP) { const T H4 = V::vmax(H, Jn); code = V::vmax(code, V::flag(H4 - H, 3)); H = H4; }
 						Hm = H + HM;
 						acc[r] = (first ? 0u : acc[r] * 16u) + (uint32_t)(pm | fL) + (uint32_t)fU;

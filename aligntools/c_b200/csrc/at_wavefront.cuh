@@ -298,9 +298,9 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 						fJ = (int)min((uint32_t)(Jn - ent), 1u);                  // stay in J only when strictly better (:660)
 					}
 					Mo = Mn + o8;
-					const int t1 = max(Ln, Mn);
-					int H = max(t1, Un);
-					code = (int)min((uint32_t)(H - Ln), 1u) + (int)min((uint32_t)(H - t1), 1u);   // first strictly greater, order L,M,U
+					int H = __vimax3_s32(Ln, Mn, Un);
+					// first strictly greater in the order L, M, U (0 / 1 / 2): notL, notM are 0 or 3; L wins -> 0, M -> 3 & 1, U -> 3 & 2
+					code = (int)min((uint32_t)(H - Ln), 3u) & ((int)min((uint32_t)(H - Mn), 3u) ^ 1);
 					if (JUMP) { const int H4 = max(H, Jn); code = max(code, (int)min((uint32_t)(H4 - H), 3u)); H = H4; }
 					Hm = H + m8;
 					acc[r] = acc[r] * 16u + (uint32_t)(pm | fL) + (uint32_t)fU;
