@@ -239,42 +239,40 @@ __global__ void __launch_bounds__(128) at_traceback_emit(const TraceArgs a)
 
 // Exclusive offsets of two per-pair count arrays (CIGAR ops, alignment columns) of a chunk:
 // off[0] = 0, off[k+1] = off[k] + cnt[k].  Block 0 scans the ops, block 1 the columns; one block of
-// 1024 threads walks its array 4096 counts at a time.  Used for chunks of up to a few 100 k pairs
+// 256 threads walks its array 2048 counts at a time.  Used for chunks of up to a few 100 k pairs
 // (larger ones go through CUB): unlike a library kernel it can be given the fill kernels'
 // shared-memory carve-out, so it runs beside a persistent fill grid of another stream.
-__global__ void __launch_bounds__(1024) at_scan_offsets(const uint32_t *cnt_ops, const uint32_t *cnt_cols, uint32_t n,
-                                                        uint64_t *off_ops, uint64_t *off_cols)
+__global__ void __launch_bounds__(256) at_scan_offsets(const uint32_t *cnt_ops, const uint32_t *cnt_cols, uint32_t n,
+                                                       uint64_t *off_ops, uint64_t *off_cols)
 {
+	// 256 threads x 8 counts per pass: small enough in threads and registers to sit beside a fill grid
+	constexpr uint32_t IPT = 8, TILE = 256 * IPT;
 	const uint32_t *cnt = blockIdx.x ? cnt_cols : cnt_ops;
 	uint64_t *off = blockIdx.x ? off_cols : off_ops;
-	__shared__ uint64_t warp_sum[32];
+	__shared__ uint64_t warp_sum[8];
 	__shared__ uint64_t carry_sh;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	if (threadIdx.x == 0) { carry_sh = 0; off[0] = 0; }
 	__syncthreads();
-	for (uint32_t base = 0; base < n; base += 4096) {
-		const uint32_t k0 = base + threadIdx.x * 4;
-		uint64_t v[4];
+	for (uint32_t base = 0; base < n; base += TILE) {
+		const uint32_t k0 = base + threadIdx.x * IPT;
+		uint64_t v[IPT];
 		uint64_t run = 0;
 #pragma unroll
-		for (int x = 0; x < 4; ++x) { run += (k0 + x < n) ? cnt[k0 + x] : 0u; v[x] = run; }
+		for (uint32_t x = 0; x < IPT; ++x) { run += (k0 + x < n) ? cnt[k0 + x] : 0u; v[x] = run; }
 		uint64_t incl = run;                                  // inclusive scan of the thread totals over the warp
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
 		if (lane == 31) warp_sum[wid] = incl;
 		__syncthreads();
-		if (wid == 0) {
-			uint64_t w = warp_sum[lane];
+		uint64_t before_warps = 0;
 #pragma unroll
-			for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += o; }
-			warp_sum[lane] = w;
-		}
-		__syncthreads();
-		const uint64_t before = carry_sh + (wid ? warp_sum[wid - 1] : 0) + (incl - run);
+		for (int w = 0; w < 8; ++w) if (w < wid) before_warps += warp_sum[w];
+		const uint64_t before = carry_sh + before_warps + (incl - run);
 #pragma unroll
-		for (int x = 0; x < 4; ++x) if (k0 + x < n) off[k0 + x + 1] = before + v[x];
+		for (uint32_t x = 0; x < IPT; ++x) if (k0 + x < n) off[k0 + x + 1] = before + v[x];
 		__syncthreads();
-		if (threadIdx.x == 1023) carry_sh = before + run;
+		if (threadIdx.x == 255) carry_sh = before + run;
 		__syncthreads();
 	}
 }

@@ -912,6 +912,9 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			int occ = 0;
 			CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * warps, dyn_smem));
 			if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, l.r); return AT_E_CUDA; }
+			// pipelined one-shot path: leave shared memory for the helper kernels of the neighbouring sub-slices
+			// (a K1 grid at full occupancy fills an SM's shared memory; nothing else could run beside it)
+			if (s.workspace && l.kind != LK_WAVE && l.kind != LK_BITS && occ > 4 && !getenv("AT_PIPE_FULL_OCC")) occ = 4;
 			int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (l.n_jobs() + warps - 1) / warps);
 			if (blocks < 1) blocks = 1;
 			const bool dom = (int)ci == dom_chunk && (int)li == dom_launch;
@@ -967,7 +970,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			s.launches++;
 			// exclusive offsets of n_ops / n_cols: offsets[0] = 0, offsets[1..nc] inclusive sums
 			if (s.workspace && nc <= (1u << 18)) {      // pipelined path: must be able to run beside another stream's fill
-				at_scan_offsets<<<2, 1024, 0, st>>>(s.d_n_ops.p + c.k0, s.d_n_cols.p + c.k0, nc, c.d_ops_off.p, c.d_cols_off.p);
+				at_scan_offsets<<<2, 256, 0, st>>>(s.d_n_ops.p + c.k0, s.d_n_cols.p + c.k0, nc, c.d_ops_off.p, c.d_cols_off.p);
 				CU(h, cudaGetLastError());
 				s.launches++;
 			} else {
