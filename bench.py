@@ -35,10 +35,10 @@ OPS_PER_CELL = {"global": 10, "local": 12, "fit": 10, "fitjump": 14, "overlap": 
 # measures 56-59 lane-ops/clk/SM for VIMNMX / LOP3 / VIADDMNMX), and one packed s16x2 instruction
 # counts as two operations.  profiles/int_peak_r01.txt has the raw numbers.
 INT32_LANES_PER_SM = 64
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per PAIR, from the ncu --set full capture
-# in profiles/ncu_fill_local_prof_r01.csv (131 072-pair launch: 90.5 MB read + 5.521 GB written); one launch of
-# the bench moves this times its number of pairs.  Algorithmic bytes: 0.5 B/cell pointers + the sequences.
-NCU_TRAFFIC_BYTES_PER_PAIR = (90.52e6 + 5.5214e9) / 131072
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per PAIR, from the ncu --set full capture of ONE
+# launch on the full 1 Mi-pair batch (profiles/ncu_fill_local_final_r01.csv: 739.2 MB read + 44.591 GB written); a launch
+# of the bench moves this times its number of pairs.  Algorithmic bytes: 0.5 B/cell pointers + the sequences.
+NCU_TRAFFIC_BYTES_PER_PAIR = (739.219456e6 + 44.591399e9) / 1048576
 PACKED_FACTOR = 2          # one s16x2 instruction advances two cells ("x2 counted for packed s16x2")
 
 
@@ -291,9 +291,9 @@ def main():
     int_peak = 148 * INT32_LANES_PER_SM * PACKED_FACTOR * sm_max_mhz * 1e6 / 1e12     # T int-op/s
     achieved = tm.fill_kernel_cells * OPS_PER_CELL["local"] / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "int_alu", "achieved": achieved, "peak": int_peak, "unit": "Tiop/s", "frac": achieved / int_peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_PAIR * args.pairs, "traffic_note": "ncu dram read+write per launch, scaled from the 131072-pair capture in profiles/",
+                "traffic": NCU_TRAFFIC_BYTES_PER_PAIR * args.pairs, "traffic_note": "ncu dram read+write of one launch (profiles/ncu_fill_local_final_r01.csv), scaled by pairs",
                 "algorithmic_bytes": int(0.5 * tm.fill_kernel_cells) + int(q.nbytes + t.nbytes),      # 4-bit pointer per cell + the sequences
-                "kernel": "at_fill_affine<LOCAL,R=5,s16x2,query-profile>", "kernel_ms": k_ms,
+                "kernel": "at_fill_affine<LOCAL,R=5,JUMP=0,PACKED=s16x2,PROF=1>", "kernel_ms": k_ms,
                 "kernel_gcups": tm.fill_kernel_cells / (k_ms * 1e-3) / 1e9,
                 "ops_per_cell": OPS_PER_CELL["local"],
                 "peak_note": (f"148 SM x {INT32_LANES_PER_SM} ALU lanes x {PACKED_FACTOR} (s16x2) x {sm_max_mhz:.0f} MHz nominal "
