@@ -200,8 +200,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if use_dist:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL logs (its version banner) go to stdout by default: rank 0 prints ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import aligntools.c_b200 as A
