@@ -80,16 +80,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		             : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
 	} while (!ok);
 }
-// Progress word of the predecessor stripe.  A relaxed (strong, L2) load, not ld.acquire: the acquire form
-// is followed by CCTL.IVALL -- an invalidation of the whole L1 -- on every poll (ncu: 13 % of all stall
-// samples of the overlap kernel).  It is not needed here: everything read after the flag (boundary blocks,
-// the local-mode chain record) is fetched with ld.global.cg, which bypasses L1, and those loads are issued
-// only after the branch on the flag's value has resolved; the producer orders its st.global.cg stores
-// before the flag with st.release.gpu.
+// Progress word of the predecessor stripe (affine kernel): polled with relaxed loads, then ONE ld.acquire once
+// the awaited column is there -- the acquire pairs with the producer's st.release.gpu and orders the boundary
+// loads behind it; polling with ld.acquire itself would invalidate L1 (CCTL.IVALL) on every iteration.
 __device__ __forceinline__ uint32_t ld_progress(const uint32_t *p)
 {
 	uint32_t v;
 	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
 // tagged hand-off words of the single-plane kernels: 64-bit accesses are single-copy atomic, so a word that
@@ -138,9 +141,10 @@ __device__ __forceinline__ void wait_columns(const uint32_t *prog, uint32_t need
 	if (lane == 0) {
 		v = ld_progress(prog);
 		while (v < need) { __nanosleep(100); v = ld_progress(prog); }
+		v = ld_acquire(prog);                  // progress only grows: still >= need
 	}
 	seen = __shfl_sync(0xffffffffu, v, 0);
-	__syncwarp();                              // the other lanes' loads are issued after lane 0 has seen the flag
+	__syncwarp();                              // orders the other lanes' loads after lane 0's acquire
 }
 
 // =====================================================================================
