@@ -151,7 +151,12 @@ struct RunWriter {
 template <bool BESIDE_FILL>
 __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 {
-	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	// Few long walks: ONE walker per warp (lane 0), so that a walk is not held back at every step by the
+	// slowest of 31 unrelated walks sharing its warp (divergent states, the odd cache miss).  Many short
+	// walks: one per thread.
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (a.lookahead && (threadIdx.x & 31u)) return;
+	const uint32_t k = a.lookahead ? gtid >> 5 : gtid;
 	if (k >= a.n_pairs) return;
 	const uint32_t p = a.pair_base + k;
 	const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
@@ -184,6 +189,11 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 			const bool go = a.mode == MODE_FIT ? (i > 0) : (i > 0 && j > 0);   // :562 | :377, :771
 			if (!go || home) break;
 			if (j == 0 && state != ST_LOW) break;         // only reachable with corrupt pointers: never index s2[-1]
+			if (state == ST_JUMP && jump) {               // a jump run reads only the 1-bit plane (32 columns per word)
+				if (a.lookahead && j > 160u) asm volatile("prefetch.global.L2 [%0];" :: "l"(pv.ptrJ + pv.rowJ + (size_t)((j - 128u + pv.lane) >> 5) * pv.RPP));
+				state = pv.jbit(j) ? ST_JUMP : ST_MID; --j; w.col(CIG_N);
+				continue;
+			}
 			if (a.lookahead) pv.prefetch(i, j, pv.half ? 2 : 3);
 			const uint32_t nb = pv.nib(j);
 			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; pv.up(); w.col(CIG_I); }

@@ -964,8 +964,9 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			ta.cigar = nullptr; ta.aln1 = nullptr; ta.aln2 = nullptr;
 			ta.mode = b->mode; ta.jump = jump ? 1 : 0;
 			ta.lookahead = nc < 32768u ? 1 : 0;       // with many short walks the chase is throughput-bound and the prefetches only add traffic
-			if (s.workspace) at_traceback_walk<true><<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
-			else at_traceback_walk<false><<<(int)((nc + 127) / 128), 128, 0, st>>>(ta);
+			const int walk_blocks = ta.lookahead ? (int)(((uint64_t)nc * 32 + 127) / 128) : (int)((nc + 127) / 128);   // one walker per warp | per thread
+			if (s.workspace) at_traceback_walk<true><<<walk_blocks, 128, 0, st>>>(ta);
+			else at_traceback_walk<false><<<walk_blocks, 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
 			// exclusive offsets of n_ops / n_cols: offsets[0] = 0, offsets[1..nc] inclusive sums
