@@ -1173,6 +1173,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 	for (auto &x : next) x = 0;
 	struct Acc { double fill = 0, tb = 0, dev = 0, domk = 0; uint64_t domc = 0, launches = 0, ptr = 0; };
 	std::vector<Acc> acc(nd * AT_PIPE_STREAMS);
+	const int n_workers = (int)std::min<uint64_t>(AT_PIPE_STREAMS, std::max<uint64_t>(1, env_u64("AT_PIPE_WORKERS", AT_PIPE_STREAMS)));   // diagnosis: fewer workers
 
 	const bool trace = getenv("AT_PIPE_TRACE") != nullptr;      // host timeline of every sub-slice on stderr
 	const auto t_origin = std::chrono::steady_clock::now();
@@ -1235,7 +1236,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 	};
 	std::vector<std::thread> th;
 	for (size_t d = 0; d < nd; ++d)
-		for (int w = 0; w < AT_PIPE_STREAMS; ++w) th.emplace_back(worker, d, w);
+		for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, d, w);
 	for (auto &t : th) t.join();
 	if (failed.load()) return failed.load();
 	uint64_t all_ops = 0, all_cols = 0;
