@@ -1,0 +1,178 @@
+// at_pipeline.inl -- the one-shot entry at_batch_align and its pipelined path; part of at_runtime.cu's
+// translation unit (included there: it uses the internal Shard / at_batch types and setup_shard /
+// run_shard / fetch_shard).
+// ------------------------------------------------------------- one-shot, pipelined ----
+// at_batch_align on a large batch: every device's slice is cut into sub-slices that go through
+// create (H2D) -> run (fill + traceback) -> fetch (D2H) on AT_PIPE_STREAMS streams, one host
+// thread per stream, so the copies of one sub-slice overlap the kernels of another.  Sub-slices
+// are claimed in pair order; a sub-slice's position in the dense CIGAR / alignment outputs is
+// known once every earlier sub-slice has finished its run (totals are published under a mutex).
+#define AT_PIPE_STREAMS 3
+static uint64_t env_u64(const char *name, uint64_t dflt) { const char *e = getenv(name); return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : dflt; }
+static uint64_t pipe_min_cells() { return env_u64("AT_PIPE_MIN_CELLS", 1ull << 31); }      // below this a batch is not worth cutting up
+static uint64_t pipe_slice_cells() { return env_u64("AT_PIPE_SLICE_CELLS", 1ull << 33); }  // target cells per full-size sub-slice (about 5 ms of fill)
+
+struct PipeSlice { uint64_t lo = 0, hi = 0; size_t dev = 0; uint64_t tot_ops = 0, tot_cols = 0; bool known = false; };
+
+static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_batch_input *in, uint32_t out_flags,
+                           at_batch_output *out, at_timing *timing, uint64_t total_cells)
+{
+	const size_t nd = h->devs.size();
+	std::lock_guard<std::mutex> one_at_a_time(h->align_mu);
+	if (h->pipe_ws.size() < nd * AT_PIPE_STREAMS) h->pipe_ws.resize(nd * AT_PIPE_STREAMS, nullptr);
+	std::vector<uint64_t> dcut;
+	cut_by_cells(in, 0, in->n_pairs, nd, dcut);
+	std::vector<PipeSlice> slices;
+	std::vector<std::vector<size_t>> per_dev(nd);
+	for (size_t d = 0; d < nd; ++d) {
+		if (dcut[d + 1] == dcut[d]) continue;
+		uint64_t cells = 0;
+		for (uint64_t k = dcut[d]; k < dcut[d + 1]; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
+		// graduated sub-slices: quarter-size units, grouped 1, 2, 4, 4, 4, ... so that the first kernel starts
+		// early (short first upload) while the bulk runs in full-size sub-slices (fewer kernel tails)
+		size_t units = (size_t)std::max<uint64_t>(1, 4 * cells / pipe_slice_cells());
+		units = std::min<size_t>(units, 256);
+		units = std::min<size_t>(units, (size_t)(dcut[d + 1] - dcut[d]));
+		std::vector<uint64_t> cut;
+		cut_by_cells(in, dcut[d], dcut[d + 1], units, cut);
+		for (size_t u0 = 0, step = 1; u0 < units; u0 += step, step = std::min<size_t>(2 * step, 4)) {
+			const size_t u1 = std::min(units, u0 + step);
+			if (cut[u1] == cut[u0]) continue;
+			PipeSlice sl; sl.lo = cut[u0]; sl.hi = cut[u1]; sl.dev = d;
+			per_dev[d].push_back(slices.size());
+			slices.push_back(sl);
+		}
+	}
+	// pipeline streams (created once per device)
+	for (size_t d = 0; d < nd; ++d) {
+		at_device &dv = h->devs[d];
+		if (!dv.pipe[0]) {
+			CU(h, cudaSetDevice(dv.id));
+			for (int w = 0; w < AT_PIPE_STREAMS; ++w) CU(h, cudaStreamCreateWithFlags(&dv.pipe[w], cudaStreamNonBlocking));
+		}
+	}
+	const bool traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
+	const bool want_cig = traceback && (out_flags & AT_OUT_CIGAR) && out->cigar;
+	const bool want_aln = traceback && (out_flags & AT_OUT_ALN) && out->aln1 && out->aln2;
+	if (want_cig && !out->cigar_off) return AT_E_ARG;
+	if (want_aln && !out->aln_off) return AT_E_ARG;
+
+	std::mutex mu; std::condition_variable cv;
+	std::atomic<int> failed{0};
+	// one sub-slice's FILL at a time owns a device's SMs: concurrent persistent fills would share them,
+	// finish together and leave the GPU idle while all workers prepare their next sub-slice in lockstep.
+	// The lock is handed on as soon as the fill has completed, so the next fill overlaps the traceback.
+	std::vector<std::mutex> run_mu(nd);
+	std::vector<std::atomic<size_t>> next(nd);
+	for (auto &x : next) x = 0;
+	struct Acc { double fill = 0, tb = 0, dev = 0, domk = 0; uint64_t domc = 0, launches = 0, ptr = 0; };
+	std::vector<Acc> acc(nd * AT_PIPE_STREAMS);
+	const int n_workers = (int)std::min<uint64_t>(AT_PIPE_STREAMS, std::max<uint64_t>(1, env_u64("AT_PIPE_WORKERS", AT_PIPE_STREAMS)));   // diagnosis: fewer workers
+
+	const bool trace = getenv("AT_PIPE_TRACE") != nullptr;      // host timeline of every sub-slice on stderr
+	const auto t_origin = std::chrono::steady_clock::now();
+	auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(); };
+	auto worker = [&](size_t d, int w) {
+		at_device &dv = h->devs[d];
+		Acc &a = acc[d * AT_PIPE_STREAMS + w];
+		// one workspace per worker, owned by the handle: the sequence buffers, pointer arena and scratch
+		// are reused by every sub-slice of this and of later calls (no allocator traffic in the pipeline)
+		at_batch *&slot = h->pipe_ws[d * AT_PIPE_STREAMS + w];
+		if (!slot) { slot = new_batch(h, mode, p, out_flags, 0); slot->shards.resize(1); }
+		at_batch *b = slot;
+		b->mode = mode; b->prm = *p; b->out_flags = out_flags;
+		b->traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
+		for (;;) {
+			const size_t k = next[d].fetch_add(1);
+			if (k >= per_dev[d].size() || failed.load()) break;
+			const size_t si = per_dev[d][k];
+			PipeSlice &sl = slices[si];
+			at_batch_input sub = *in;
+			sub.n_pairs = sl.hi - sl.lo;
+			sub.q_off = in->q_off + sl.lo; sub.q_len = in->q_len + sl.lo;
+			sub.t_off = in->t_off + sl.lo; sub.t_len = in->t_len + sl.lo;
+			if (in->site_off) sub.site_off = in->site_off + sl.lo;
+			b->n = sub.n_pairs;
+			Shard &s = b->shards[0];
+			s.dev = &dv; s.stream = dv.pipe[w]; s.workspace = true; s.p0 = 0; s.p1 = sub.n_pairs; s.n = (uint32_t)sub.n_pairs; s.out_base = sl.lo;
+			const double t_a = now_ms();
+			int rc = setup_shard(b, s, &sub);
+			const double t_b = now_ms();
+			if (!rc) {
+				std::unique_lock<std::mutex> own(run_mu[d]);
+				const std::function<void()> hand_on = [&] { if (own.owns_lock()) own.unlock(); };
+				rc = run_shard(b, s, &hand_on);
+			}
+			const double t_c = now_ms();
+			uint64_t to = 0, tc = 0;
+			if (!rc) for (auto &c : s.chunks) { to += c.tot_ops; tc += c.tot_cols; }
+			uint64_t base_ops = 0, base_cols = 0;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				sl.tot_ops = to; sl.tot_cols = tc; sl.known = true;
+				if (rc) failed = rc;
+				cv.notify_all();
+				cv.wait(lk, [&] { if (failed.load()) return true; for (size_t x = 0; x < si; ++x) if (!slices[x].known) return false; return true; });
+				for (size_t x = 0; x < si; ++x) { base_ops += slices[x].tot_ops; base_cols += slices[x].tot_cols; }
+			}
+			if (!rc && !failed.load()) {
+				if ((want_cig && base_ops + to > out->cigar_cap) || (want_aln && base_cols + tc > out->aln_cap)) {
+					set_err(h, "output buffer too small: need at least %llu ops / %llu bytes", (unsigned long long)(base_ops + to), (unsigned long long)(base_cols + tc));
+					rc = AT_E_NOSPACE;
+				} else rc = fetch_shard(b, s, out, want_cig, want_aln, base_ops, base_cols);
+			}
+			if (trace) fprintf(stderr, "[at pipe] dev %zu stream %d slice %zu pairs %llu: setup %.2f-%.2f run -%.2f fetch -%.2f ms (fill %.2f tb %.2f)\n",
+			                   d, w, si, (unsigned long long)sub.n_pairs, t_a, t_b, t_c, now_ms(), s.fill_ms, s.tb_ms);
+			a.fill += s.fill_ms; a.tb += s.tb_ms; a.dev += s.dev_ms; a.launches += s.launches; a.ptr += traceback ? s.ptr_bytes : 0;
+			if (s.domk_cells > a.domc) { a.domc = s.domk_cells; a.domk = s.domk_ms; }
+			if (rc) { std::lock_guard<std::mutex> lk(mu); failed = rc; cv.notify_all(); break; }
+		}
+	};
+	std::vector<std::thread> th;
+	for (size_t d = 0; d < nd; ++d)
+		for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, d, w);
+	for (auto &t : th) t.join();
+	if (failed.load()) return failed.load();
+	uint64_t all_ops = 0, all_cols = 0;
+	for (auto &sl : slices) { all_ops += sl.tot_ops; all_cols += sl.tot_cols; }
+	if (want_cig) out->cigar_off[in->n_pairs] = all_ops;
+	if (want_aln) out->aln_off[in->n_pairs] = all_cols;
+	if (!traceback) {
+		if (out->cigar_off) for (uint64_t k = 0; k <= in->n_pairs; ++k) out->cigar_off[k] = 0;
+		if (out->aln_off) for (uint64_t k = 0; k <= in->n_pairs; ++k) out->aln_off[k] = 0;
+	}
+	if (timing) {
+		memset(timing, 0, sizeof *timing);
+		timing->cells = total_cells;
+		for (size_t d = 0; d < nd; ++d) {
+			double fill = 0, tb = 0, dev = 0;
+			for (int w = 0; w < AT_PIPE_STREAMS; ++w) {
+				const Acc &a = acc[d * AT_PIPE_STREAMS + w];
+				fill += a.fill; tb += a.tb; dev += a.dev; timing->launches += a.launches; timing->ptr_bytes += a.ptr;
+				if (a.domc > timing->fill_kernel_cells) { timing->fill_kernel_cells = a.domc; timing->fill_kernel_ms = a.domk; }
+			}
+			timing->fill_ms = std::max(timing->fill_ms, fill); timing->traceback_ms = std::max(timing->traceback_ms, tb);
+			timing->device_ms = std::max(timing->device_ms, dev);     // sum of the sub-slices' device times (they overlap)
+		}
+	}
+	return AT_OK;
+}
+
+extern "C" int at_batch_align(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
+                              uint32_t out_flags, at_batch_output *out, at_timing *timing)
+{
+	if (!h || !p || !in || !out || !out->score) return AT_E_ARG;
+	if (int rc = validate_batch(h, mode, p, in)) return rc;
+	uint64_t cells = 0;
+	for (uint64_t k = 0; k < in->n_pairs; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
+	if (cells >= pipe_min_cells() && in->n_pairs >= 16 && !getenv("AT_NO_PIPELINE"))
+		return align_pipelined(h, mode, p, in, out_flags, out, timing, cells);
+	at_batch *b = nullptr;
+	int rc = at_batch_create(h, mode, p, in, out_flags, &b);
+	if (rc) return rc;
+	rc = at_batch_run(b, timing);
+	if (!rc) rc = at_batch_fetch(b, out);
+	at_batch_free(b);
+	return rc;
+}
+

@@ -9,6 +9,7 @@
 // entry returns AT_E_CUDA.
 #include "../../../include/aligntools_b200.h"
 #include "at_kernels.cuh"
+#include "at_devmem.h"
 
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
@@ -31,30 +32,6 @@
 using namespace at;
 
 // ------------------------------------------------------------------ handle ----
-// Large device blocks (the traceback-pointer arena: tens of GB) come from plain cudaMalloc and are kept
-// in a per-device cache for the life of the handle.  The stream-ordered pool maps such a block at about
-// 20 GB/s the first time (seconds for one arena); cudaMalloc takes milliseconds.
-struct BigCache {
-	struct Blk { void *p; size_t bytes; };
-	std::mutex mu;
-	std::vector<Blk> free_blocks;
-	void *take(size_t bytes, size_t *got) {
-		std::lock_guard<std::mutex> g(mu);
-		size_t best = SIZE_MAX;
-		for (size_t k = 0; k < free_blocks.size(); ++k)
-			if (free_blocks[k].bytes >= bytes && free_blocks[k].bytes <= 2 * bytes &&
-			    (best == SIZE_MAX || free_blocks[k].bytes < free_blocks[best].bytes)) best = k;
-		if (best == SIZE_MAX) return nullptr;
-		void *p = free_blocks[best].p; *got = free_blocks[best].bytes;
-		free_blocks.erase(free_blocks.begin() + best);
-		return p;
-	}
-	void give(void *p, size_t bytes) { std::lock_guard<std::mutex> g(mu); free_blocks.push_back(Blk{p, bytes}); }
-	void drop_all() { std::lock_guard<std::mutex> g(mu); for (auto &b : free_blocks) cudaFree(b.p); free_blocks.clear(); }
-	size_t cached_bytes() { std::lock_guard<std::mutex> g(mu); size_t t = 0; for (auto &b : free_blocks) t += b.bytes; return t; }
-};
-static const size_t AT_BIG_BLOCK = 256ull << 20;
-
 struct at_device {
 	int id = 0;
 	int sm_count = 0;
@@ -170,72 +147,6 @@ extern "C" int at_device_count(const at_handle *h) { return h ? (int)h->devs.siz
 extern "C" uint64_t at_launch_count(const at_handle *h) { return h ? h->launches.load() : 0; }
 
 // ------------------------------------------------------------------- batch ----
-// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync); at_create
-// raises the pool's release threshold so that the 40+ GB pointer arena of one batch is handed to
-// the next batch without going back to the driver.  tl_stream is the calling shard's stream.
-static thread_local cudaStream_t tl_stream = nullptr;
-
-// A shard (in the pipelined one-shot path: a worker's workspace) keeps the blocks it releases in a
-// small cache and reuses them for its next allocations, so a steady-state sub-slice makes NO call into
-// the CUDA allocator: cudaMallocAsync / cudaFreeAsync from several streams make the pool insert
-// cross-stream dependencies (or map new memory), which coupled the pipeline workers' streams.
-struct BufCache {
-	struct Blk { void *p; size_t bytes; };
-	std::vector<Blk> free_blocks;
-	void *take(size_t bytes) {
-		size_t best = SIZE_MAX;
-		for (size_t k = 0; k < free_blocks.size(); ++k)
-			if (free_blocks[k].bytes >= bytes && free_blocks[k].bytes <= 4 * bytes + 4096 &&
-			    (best == SIZE_MAX || free_blocks[k].bytes < free_blocks[best].bytes)) best = k;
-		if (best == SIZE_MAX) return nullptr;
-		void *p = free_blocks[best].p;
-		last_bytes = free_blocks[best].bytes;
-		free_blocks.erase(free_blocks.begin() + best);
-		return p;
-	}
-	size_t last_bytes = 0;
-	void give(void *p, size_t bytes) { free_blocks.push_back(Blk{p, bytes}); }
-	void flush(cudaStream_t st) { for (auto &b : free_blocks) cudaFreeAsync(b.p, st); free_blocks.clear(); }
-};
-static thread_local BufCache *tl_cache = nullptr;
-static thread_local BigCache *tl_big = nullptr;
-
-template <class T> struct DevBuf {
-	T *p = nullptr; size_t n = 0; size_t bytes = 0; bool big = false;
-	cudaError_t alloc(size_t count) {
-		if (count <= n && p) return cudaSuccess;
-		release();
-		const size_t want = std::max<size_t>(count, 1) * sizeof(T);
-		if (want >= AT_BIG_BLOCK && tl_big) {          // arena-sized: cudaMalloc, cached per device
-			size_t got = 0;
-			void *q = tl_big->take(want, &got);
-			cudaError_t e = cudaSuccess;
-			if (!q) {
-				got = want;
-				e = cudaMalloc(&q, want);
-				if (e != cudaSuccess) { cudaGetLastError(); tl_big->drop_all(); e = cudaMalloc(&q, want); }   // cached blocks may be in the way
-			}
-			if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return e; }
-			p = (T *)q; bytes = got; n = got / sizeof(T); big = true;
-			return cudaSuccess;
-		}
-		if (tl_cache) { if (void *q = tl_cache->take(want)) { p = (T *)q; bytes = tl_cache->last_bytes; n = bytes / sizeof(T); return cudaSuccess; } }
-		cudaError_t e = cudaMallocAsync((void **)&p, want, tl_stream);
-		if (e != cudaSuccess && tl_big) { cudaGetLastError(); tl_big->drop_all(); e = cudaMallocAsync((void **)&p, want, tl_stream); }   // cached arenas may be in the way
-		if (e == cudaSuccess) { n = count; bytes = want; } else { p = nullptr; cudaGetLastError(); }
-		return e;
-	}
-	void release() {
-		if (p) {
-			if (big && tl_big) tl_big->give(p, bytes);
-			else if (big) cudaFree(p);
-			else if (tl_cache) tl_cache->give(p, bytes);
-			else cudaFreeAsync(p, tl_stream);
-		}
-		p = nullptr; n = 0; bytes = 0; big = false;
-	}
-};
-
 static const int MAXR = 8;
 static const size_t AT_SEQ_SLACK = 1024;   // K2 stages 256-byte target tiles by TMA: the last tile may run past the last record
 
@@ -421,6 +332,90 @@ extern "C" void at_batch_free(at_batch *b)
 	delete b;
 }
 
+// Which bytes occur in a device buffer (at_symbol_set): 256-bit set, read back to the host.
+static int scan_alphabet(at_handle *h, Shard &s, const uint8_t *d_bytes, uint64_t n_bytes, uint32_t set8[8])
+{
+	cudaStream_t st = s.stream;
+	CU(h, s.d_symset.alloc(8));
+	CU(h, cudaMemsetAsync(s.d_symset.p, 0, 8 * sizeof(uint32_t), st));
+	at_symbol_set<<<(int)std::min<uint64_t>(s.dev->sm_count * 8, (n_bytes + 4095) / 4096 + 1), 256, 0, st>>>(d_bytes, n_bytes, s.d_symset.p);
+	CU(h, cudaGetLastError());
+	h->launches++;
+	CU(h, cudaMemcpyAsync(set8, s.d_symset.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CU(h, cudaStreamSynchronize(st));
+	return AT_OK;
+}
+
+static int upload_symmap(at_handle *h, Shard &s, const uint8_t map[256])
+{
+	CU(h, s.d_symmap.alloc(256));
+	CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, s.stream));
+	CU(h, cudaStreamSynchronize(s.stream));
+	return AT_OK;
+}
+
+// Kernel variants of the shard, from the alphabets of its sequences:
+//   s.prof  query-profile variant of K1 / K2 -- the TARGETS use at most 4 distinct bytes (symmap: target byte -> 0..3);
+//   s.bits  bit-parallel kernel for `edit -u 1` -- the READS use at most 8 distinct bytes (symmap: read byte -> 0..7,
+//           anything else -> 8).  The two are exclusive: symmap describes one side.
+static int choose_variants(at_batch *b, Shard &s, const at_batch_input *in, uint64_t q_span)
+{
+	at_handle *h = b->h;
+	int rc;
+	s.prof = false; s.bits = false; s.syms = 0;
+	const bool two_bit = in->encoding == AT_SEQ_2BIT;                  // the alphabet is ACGT by construction
+	uint32_t set8[8];
+	uint8_t map[256];
+	if (b->mode == AT_EDIT && b->prm.u == 1 && !getenv("AT_NO_BITPAR")) {
+		memset(map, 8, sizeof map);
+		int nsym = 0;
+		if (two_bit) { map['A'] = 0; map['C'] = 1; map['G'] = 2; map['T'] = 3; nsym = 4; }
+		else {
+			if ((rc = scan_alphabet(h, s, s.d_q.p, q_span, set8))) return rc;
+			for (int c = 0; c < 256; ++c)
+				if (set8[c >> 5] >> (c & 31) & 1u) { if (nsym < 8) map[c] = (uint8_t)nsym; ++nsym; }
+		}
+		if (nsym >= 1 && nsym <= 8) { s.bits = true; return upload_symmap(h, s, map); }
+		return AT_OK;                                                  // large read alphabet: cell-by-cell kernel, xor/min variant
+	}
+	if (getenv("AT_NO_PROFILE")) return AT_OK;
+	memset(map, 0, sizeof map);
+	int nsym = 0; uint32_t syms = 0;
+	if (two_bit) { map['C'] = 1; map['G'] = 2; map['T'] = 3; nsym = 4; syms = (uint32_t)'A' | ((uint32_t)'C' << 8) | ((uint32_t)'G' << 16) | ((uint32_t)'T' << 24); }
+	else {
+		// d_t holds the caller's span: every byte of it is a target byte or a gap between records (which can only add symbols)
+		if ((rc = scan_alphabet(h, s, s.d_t.p, s.t_span, set8))) return rc;
+		for (int c = 0; c < 256; ++c)
+			if (set8[c >> 5] >> (c & 31) & 1u) { if (nsym < 4) { map[c] = (uint8_t)nsym; syms |= (uint32_t)c << (8 * nsym); } ++nsym; }
+	}
+	if (nsym < 1 || nsym > 4) return AT_OK;
+	for (int c = nsym; c < 4; ++c) syms |= (syms & 255u) << (8 * c);   // unused codes repeat a used symbol (they are never looked up)
+	s.syms = syms; s.prof = true;
+	return upload_symmap(h, s, map);
+}
+
+// fit+jump: the per-pair blacklists as a byte mask aligned with the target bytes (at_build_jmask)
+static int build_jump_mask(at_batch *b, Shard &s, const at_batch_input *in)
+{
+	at_handle *h = b->h;
+	cudaStream_t st = s.stream;
+	const uint32_t n = s.n;
+	CU(h, s.d_jmask.alloc(s.d_t.n));
+	CU(h, cudaMemsetAsync(s.d_jmask.p, 0, s.d_t.n, st));
+	if (!in->sites || !in->site_off) return AT_OK;
+	const uint64_t lo = in->site_off[s.p0], hi = in->site_off[s.p1];
+	std::vector<uint64_t> so(n + 1);
+	for (uint32_t k = 0; k <= n; ++k) so[k] = in->site_off[s.p0 + k] - lo;
+	CU(h, s.d_sites.alloc(hi - lo + 1)); CU(h, s.d_site_off.alloc(n + 1));
+	if (hi > lo) CU(h, cudaMemcpyAsync(s.d_sites.p, in->sites + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	CU(h, cudaMemcpyAsync(s.d_site_off.p, so.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, s.d_t_off.p, s.d_t_len.p, n, s.d_jmask.p);
+	CU(h, cudaGetLastError());
+	h->launches++;
+	CU(h, cudaStreamSynchronize(st));
+	return AT_OK;
+}
+
 static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 {
 	at_handle *h = b->h;
@@ -446,84 +441,8 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	s.d_q2.release(); s.d_t2.release();
 	mark("upload");
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
-	// target alphabet of the shard -> query-profile variant of K1 (affine modes) when it has at most 4 symbols
-	s.prof = false; s.syms = 0;
-	const bool bits_wanted = b->mode == AT_EDIT && b->prm.u == 1 && !getenv("AT_NO_BITPAR");      // then symmap describes the reads instead
-	if (!bits_wanted && in->encoding == AT_SEQ_2BIT) {
-		uint8_t map[256]; memset(map, 0, sizeof map);
-		map['C'] = 1; map['G'] = 2; map['T'] = 3;
-		s.syms = (uint32_t)'A' | ((uint32_t)'C' << 8) | ((uint32_t)'G' << 16) | ((uint32_t)'T' << 24);
-		CU(h, s.d_symmap.alloc(256));
-		CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, st));
-		CU(h, cudaStreamSynchronize(st));
-		s.prof = !getenv("AT_NO_PROFILE");
-	} else if (!bits_wanted && !getenv("AT_NO_PROFILE")) {
-		uint32_t set8[8];
-		CU(h, s.d_symset.alloc(8));
-		CU(h, cudaMemsetAsync(s.d_symset.p, 0, 8 * sizeof(uint32_t), st));
-		// d_t holds the caller's span [lo, hi): every byte of it is a target byte or the gap between records
-		at_symbol_set<<<(int)std::min<uint64_t>(s.dev->sm_count * 8, (s.t_span + 4095) / 4096 + 1), 256, 0, st>>>(s.d_t.p, s.t_span, s.d_symset.p);
-		CU(h, cudaGetLastError());
-		h->launches++;
-		CU(h, cudaMemcpyAsync(set8, s.d_symset.p, sizeof set8, cudaMemcpyDeviceToHost, st));
-		CU(h, cudaStreamSynchronize(st));
-		uint8_t map[256]; memset(map, 0, sizeof map);
-		int nsym = 0; uint32_t syms = 0;
-		for (int c = 0; c < 256; ++c)
-			if (set8[c >> 5] >> (c & 31) & 1u) { if (nsym < 4) { map[c] = (uint8_t)nsym; syms |= (uint32_t)c << (8 * nsym); } ++nsym; }
-		if (nsym >= 1 && nsym <= 4) {
-			// unused codes must not equal any read byte by accident: point them at a used symbol
-			for (int c = nsym; c < 4; ++c) syms |= (syms & 255u) << (8 * c);
-			s.syms = syms; s.prof = true;
-			CU(h, s.d_symmap.alloc(256));
-			CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, st));
-			CU(h, cudaStreamSynchronize(st));
-		}
-	}
-	if (jump) {
-		uint64_t tot_t = 0;
-		for (uint32_t k = 0; k < n; ++k) tot_t += in->t_len[s.p0 + k];
-		CU(h, s.d_jmask.alloc(s.d_t.n));
-		CU(h, cudaMemsetAsync(s.d_jmask.p, 0, s.d_t.n, st));
-		if (in->sites && in->site_off) {
-			const uint64_t lo = in->site_off[s.p0], hi = in->site_off[s.p1];
-			std::vector<uint64_t> so(n + 1);
-			for (uint32_t k = 0; k <= n; ++k) so[k] = in->site_off[s.p0 + k] - lo;
-			CU(h, s.d_sites.alloc(hi - lo + 1)); CU(h, s.d_site_off.alloc(n + 1));
-			if (hi > lo) CU(h, cudaMemcpyAsync(s.d_sites.p, in->sites + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-			CU(h, cudaMemcpyAsync(s.d_site_off.p, so.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-			at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, s.d_t_off.p, s.d_t_len.p, n, s.d_jmask.p);
-			CU(h, cudaGetLastError());
-			h->launches++;
-			CU(h, cudaStreamSynchronize(st));
-		}
-		(void)tot_t;
-	}
-	// edit -u 1 on a small read alphabet: the bit-parallel kernel (Myers); symmap: read byte -> 0..7, anything else -> 8
-	s.bits = false;
-	if (b->mode == AT_EDIT && b->prm.u == 1 && !getenv("AT_NO_BITPAR")) {
-		uint8_t map[256]; memset(map, 8, sizeof map);
-		int nsym = 0;
-		if (in->encoding == AT_SEQ_2BIT) { map['A'] = 0; map['C'] = 1; map['G'] = 2; map['T'] = 3; nsym = 4; }
-		else {
-			uint32_t set8[8];
-			CU(h, s.d_symset.alloc(8));
-			CU(h, cudaMemsetAsync(s.d_symset.p, 0, 8 * sizeof(uint32_t), st));
-			at_symbol_set<<<(int)std::min<uint64_t>(s.dev->sm_count * 8, (q_span + 4095) / 4096 + 1), 256, 0, st>>>(s.d_q.p, q_span, s.d_symset.p);
-			CU(h, cudaGetLastError());
-			h->launches++;
-			CU(h, cudaMemcpyAsync(set8, s.d_symset.p, sizeof set8, cudaMemcpyDeviceToHost, st));
-			CU(h, cudaStreamSynchronize(st));
-			for (int c = 0; c < 256; ++c)
-				if (set8[c >> 5] >> (c & 31) & 1u) { if (nsym < 8) map[c] = (uint8_t)nsym; ++nsym; }
-		}
-		if (nsym >= 1 && nsym <= 8) {
-			s.bits = true;
-			CU(h, s.d_symmap.alloc(256));
-			CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, st));
-			CU(h, cudaStreamSynchronize(st));
-		}
-	}
+	if ((rc = choose_variants(b, s, in, q_span))) return rc;
+	if (jump && (rc = build_jump_mask(b, s, in))) return rc;
 	mark("alphabet+jmask");
 	// per-pair class, result arrays
 	s.h_rclass.resize(n);
@@ -1107,180 +1026,7 @@ extern "C" int at_batch_fetch(at_batch *b, at_batch_output *out)
 	return AT_OK;
 }
 
-// ------------------------------------------------------------- one-shot, pipelined ----
-// at_batch_align on a large batch: every device's slice is cut into sub-slices that go through
-// create (H2D) -> run (fill + traceback) -> fetch (D2H) on AT_PIPE_STREAMS streams, one host
-// thread per stream, so the copies of one sub-slice overlap the kernels of another.  Sub-slices
-// are claimed in pair order; a sub-slice's position in the dense CIGAR / alignment outputs is
-// known once every earlier sub-slice has finished its run (totals are published under a mutex).
-#define AT_PIPE_STREAMS 3
-static uint64_t env_u64(const char *name, uint64_t dflt) { const char *e = getenv(name); return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : dflt; }
-static uint64_t pipe_min_cells() { return env_u64("AT_PIPE_MIN_CELLS", 1ull << 31); }      // below this a batch is not worth cutting up
-static uint64_t pipe_slice_cells() { return env_u64("AT_PIPE_SLICE_CELLS", 1ull << 33); }  // target cells per full-size sub-slice (about 5 ms of fill)
-
-struct PipeSlice { uint64_t lo = 0, hi = 0; size_t dev = 0; uint64_t tot_ops = 0, tot_cols = 0; bool known = false; };
-
-static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_batch_input *in, uint32_t out_flags,
-                           at_batch_output *out, at_timing *timing, uint64_t total_cells)
-{
-	const size_t nd = h->devs.size();
-	std::lock_guard<std::mutex> one_at_a_time(h->align_mu);
-	if (h->pipe_ws.size() < nd * AT_PIPE_STREAMS) h->pipe_ws.resize(nd * AT_PIPE_STREAMS, nullptr);
-	std::vector<uint64_t> dcut;
-	cut_by_cells(in, 0, in->n_pairs, nd, dcut);
-	std::vector<PipeSlice> slices;
-	std::vector<std::vector<size_t>> per_dev(nd);
-	for (size_t d = 0; d < nd; ++d) {
-		if (dcut[d + 1] == dcut[d]) continue;
-		uint64_t cells = 0;
-		for (uint64_t k = dcut[d]; k < dcut[d + 1]; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
-		// graduated sub-slices: quarter-size units, grouped 1, 2, 4, 4, 4, ... so that the first kernel starts
-		// early (short first upload) while the bulk runs in full-size sub-slices (fewer kernel tails)
-		size_t units = (size_t)std::max<uint64_t>(1, 4 * cells / pipe_slice_cells());
-		units = std::min<size_t>(units, 256);
-		units = std::min<size_t>(units, (size_t)(dcut[d + 1] - dcut[d]));
-		std::vector<uint64_t> cut;
-		cut_by_cells(in, dcut[d], dcut[d + 1], units, cut);
-		for (size_t u0 = 0, step = 1; u0 < units; u0 += step, step = std::min<size_t>(2 * step, 4)) {
-			const size_t u1 = std::min(units, u0 + step);
-			if (cut[u1] == cut[u0]) continue;
-			PipeSlice sl; sl.lo = cut[u0]; sl.hi = cut[u1]; sl.dev = d;
-			per_dev[d].push_back(slices.size());
-			slices.push_back(sl);
-		}
-	}
-	// pipeline streams (created once per device)
-	for (size_t d = 0; d < nd; ++d) {
-		at_device &dv = h->devs[d];
-		if (!dv.pipe[0]) {
-			CU(h, cudaSetDevice(dv.id));
-			for (int w = 0; w < AT_PIPE_STREAMS; ++w) CU(h, cudaStreamCreateWithFlags(&dv.pipe[w], cudaStreamNonBlocking));
-		}
-	}
-	const bool traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
-	const bool want_cig = traceback && (out_flags & AT_OUT_CIGAR) && out->cigar;
-	const bool want_aln = traceback && (out_flags & AT_OUT_ALN) && out->aln1 && out->aln2;
-	if (want_cig && !out->cigar_off) return AT_E_ARG;
-	if (want_aln && !out->aln_off) return AT_E_ARG;
-
-	std::mutex mu; std::condition_variable cv;
-	std::atomic<int> failed{0};
-	// one sub-slice's FILL at a time owns a device's SMs: concurrent persistent fills would share them,
-	// finish together and leave the GPU idle while all workers prepare their next sub-slice in lockstep.
-	// The lock is handed on as soon as the fill has completed, so the next fill overlaps the traceback.
-	std::vector<std::mutex> run_mu(nd);
-	std::vector<std::atomic<size_t>> next(nd);
-	for (auto &x : next) x = 0;
-	struct Acc { double fill = 0, tb = 0, dev = 0, domk = 0; uint64_t domc = 0, launches = 0, ptr = 0; };
-	std::vector<Acc> acc(nd * AT_PIPE_STREAMS);
-	const int n_workers = (int)std::min<uint64_t>(AT_PIPE_STREAMS, std::max<uint64_t>(1, env_u64("AT_PIPE_WORKERS", AT_PIPE_STREAMS)));   // diagnosis: fewer workers
-
-	const bool trace = getenv("AT_PIPE_TRACE") != nullptr;      // host timeline of every sub-slice on stderr
-	const auto t_origin = std::chrono::steady_clock::now();
-	auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(); };
-	auto worker = [&](size_t d, int w) {
-		at_device &dv = h->devs[d];
-		Acc &a = acc[d * AT_PIPE_STREAMS + w];
-		// one workspace per worker, owned by the handle: the sequence buffers, pointer arena and scratch
-		// are reused by every sub-slice of this and of later calls (no allocator traffic in the pipeline)
-		at_batch *&slot = h->pipe_ws[d * AT_PIPE_STREAMS + w];
-		if (!slot) { slot = new_batch(h, mode, p, out_flags, 0); slot->shards.resize(1); }
-		at_batch *b = slot;
-		b->mode = mode; b->prm = *p; b->out_flags = out_flags;
-		b->traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
-		for (;;) {
-			const size_t k = next[d].fetch_add(1);
-			if (k >= per_dev[d].size() || failed.load()) break;
-			const size_t si = per_dev[d][k];
-			PipeSlice &sl = slices[si];
-			at_batch_input sub = *in;
-			sub.n_pairs = sl.hi - sl.lo;
-			sub.q_off = in->q_off + sl.lo; sub.q_len = in->q_len + sl.lo;
-			sub.t_off = in->t_off + sl.lo; sub.t_len = in->t_len + sl.lo;
-			if (in->site_off) sub.site_off = in->site_off + sl.lo;
-			b->n = sub.n_pairs;
-			Shard &s = b->shards[0];
-			s.dev = &dv; s.stream = dv.pipe[w]; s.workspace = true; s.p0 = 0; s.p1 = sub.n_pairs; s.n = (uint32_t)sub.n_pairs; s.out_base = sl.lo;
-			const double t_a = now_ms();
-			int rc = setup_shard(b, s, &sub);
-			const double t_b = now_ms();
-			if (!rc) {
-				std::unique_lock<std::mutex> own(run_mu[d]);
-				const std::function<void()> hand_on = [&] { if (own.owns_lock()) own.unlock(); };
-				rc = run_shard(b, s, &hand_on);
-			}
-			const double t_c = now_ms();
-			uint64_t to = 0, tc = 0;
-			if (!rc) for (auto &c : s.chunks) { to += c.tot_ops; tc += c.tot_cols; }
-			uint64_t base_ops = 0, base_cols = 0;
-			{
-				std::unique_lock<std::mutex> lk(mu);
-				sl.tot_ops = to; sl.tot_cols = tc; sl.known = true;
-				if (rc) failed = rc;
-				cv.notify_all();
-				cv.wait(lk, [&] { if (failed.load()) return true; for (size_t x = 0; x < si; ++x) if (!slices[x].known) return false; return true; });
-				for (size_t x = 0; x < si; ++x) { base_ops += slices[x].tot_ops; base_cols += slices[x].tot_cols; }
-			}
-			if (!rc && !failed.load()) {
-				if ((want_cig && base_ops + to > out->cigar_cap) || (want_aln && base_cols + tc > out->aln_cap)) {
-					set_err(h, "output buffer too small: need at least %llu ops / %llu bytes", (unsigned long long)(base_ops + to), (unsigned long long)(base_cols + tc));
-					rc = AT_E_NOSPACE;
-				} else rc = fetch_shard(b, s, out, want_cig, want_aln, base_ops, base_cols);
-			}
-			if (trace) fprintf(stderr, "[at pipe] dev %zu stream %d slice %zu pairs %llu: setup %.2f-%.2f run -%.2f fetch -%.2f ms (fill %.2f tb %.2f)\n",
-			                   d, w, si, (unsigned long long)sub.n_pairs, t_a, t_b, t_c, now_ms(), s.fill_ms, s.tb_ms);
-			a.fill += s.fill_ms; a.tb += s.tb_ms; a.dev += s.dev_ms; a.launches += s.launches; a.ptr += traceback ? s.ptr_bytes : 0;
-			if (s.domk_cells > a.domc) { a.domc = s.domk_cells; a.domk = s.domk_ms; }
-			if (rc) { std::lock_guard<std::mutex> lk(mu); failed = rc; cv.notify_all(); break; }
-		}
-	};
-	std::vector<std::thread> th;
-	for (size_t d = 0; d < nd; ++d)
-		for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, d, w);
-	for (auto &t : th) t.join();
-	if (failed.load()) return failed.load();
-	uint64_t all_ops = 0, all_cols = 0;
-	for (auto &sl : slices) { all_ops += sl.tot_ops; all_cols += sl.tot_cols; }
-	if (want_cig) out->cigar_off[in->n_pairs] = all_ops;
-	if (want_aln) out->aln_off[in->n_pairs] = all_cols;
-	if (!traceback) {
-		if (out->cigar_off) for (uint64_t k = 0; k <= in->n_pairs; ++k) out->cigar_off[k] = 0;
-		if (out->aln_off) for (uint64_t k = 0; k <= in->n_pairs; ++k) out->aln_off[k] = 0;
-	}
-	if (timing) {
-		memset(timing, 0, sizeof *timing);
-		timing->cells = total_cells;
-		for (size_t d = 0; d < nd; ++d) {
-			double fill = 0, tb = 0, dev = 0;
-			for (int w = 0; w < AT_PIPE_STREAMS; ++w) {
-				const Acc &a = acc[d * AT_PIPE_STREAMS + w];
-				fill += a.fill; tb += a.tb; dev += a.dev; timing->launches += a.launches; timing->ptr_bytes += a.ptr;
-				if (a.domc > timing->fill_kernel_cells) { timing->fill_kernel_cells = a.domc; timing->fill_kernel_ms = a.domk; }
-			}
-			timing->fill_ms = std::max(timing->fill_ms, fill); timing->traceback_ms = std::max(timing->traceback_ms, tb);
-			timing->device_ms = std::max(timing->device_ms, dev);     // sum of the sub-slices' device times (they overlap)
-		}
-	}
-	return AT_OK;
-}
-
-extern "C" int at_batch_align(at_handle *h, int mode, const at_params *p, const at_batch_input *in,
-                              uint32_t out_flags, at_batch_output *out, at_timing *timing)
-{
-	if (!h || !p || !in || !out || !out->score) return AT_E_ARG;
-	if (int rc = validate_batch(h, mode, p, in)) return rc;
-	uint64_t cells = 0;
-	for (uint64_t k = 0; k < in->n_pairs; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
-	if (cells >= pipe_min_cells() && in->n_pairs >= 16 && !getenv("AT_NO_PIPELINE"))
-		return align_pipelined(h, mode, p, in, out_flags, out, timing, cells);
-	at_batch *b = nullptr;
-	int rc = at_batch_create(h, mode, p, in, out_flags, &b);
-	if (rc) return rc;
-	rc = at_batch_run(b, timing);
-	if (!rc) rc = at_batch_fetch(b, out);
-	at_batch_free(b);
-	return rc;
-}
+#include "at_pipeline.inl"      // at_batch_align: the pipelined one-shot path (same translation unit)
 
 extern "C" int64_t at_pack_2bit(const char *seq, uint64_t n, uint8_t *dst)
 {
