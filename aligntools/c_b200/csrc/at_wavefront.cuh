@@ -25,6 +25,7 @@
 // Reference recurrences: src/alignment.h:451-462 (global), :635-667 (fit), :825-841 (local),
 // :940-949 (overlap), :303-311 (edit); tie rules SURVEY.md A.0.
 #pragma once
+#include <type_traits>
 
 namespace at {
 
@@ -251,7 +252,10 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 		}
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
 
-		auto step = [&](const uint32_t t, const bool checked) {
+		// `cap`: std::true_type in the pair's last stripe -- only there can a lane hold the row whose cells the
+		// end-cell search looks at; the other stripes run a body without those compares and selects
+		auto step = [&](const uint32_t t, const bool checked, auto cap) {
+			constexpr bool CAP = decltype(cap)::value;
 			const int j = (int)t - lane;
 			int rM = __shfl_up_sync(0xffffffffu, sM, 1);
 			int rL = __shfl_up_sync(0xffffffffu, sL, 1);
@@ -310,13 +314,13 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 					acc[r] = acc[r] * 16u + (uint32_t)(pm | fL) + (uint32_t)fU;
 					if (JUMP) accJ[r] = accJ[r] * 2u + (uint32_t)fJ;
 					if (MODE == MODE_LOCAL) kbest = __viaddmax_s32(Mn, crow[r], kbest);
-					if (MODE == MODE_FIT) {
+					if (MODE == MODE_FIT && CAP) {
 						if (r == cap_r && j < (int)l2) {                         // column l2 excluded (:677, :684)
 							if (Mn > capM) { capM = Mn; capMj = j; }
 							if (Ln > capL) { capL = Ln; capLj = j; }
 						}
 					}
-					if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) { gH = H; gC = code; } }
+					if (MODE == MODE_GLOBAL && CAP) { if (r == cap_r && j == (int)l2) { gH = H; gC = code; } }
 					D = Hl[r]; DC = Cl[r];
 					Hl[r] = Hm; Cl[r] = code; Ul[r] = Un; Mol[r] = Mo; if (JUMP) Jl[r] = Jn;
 					Lup = Ln; MoUp = Mo;
@@ -361,11 +365,16 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 			// two steps per loop body: 8 rows x 2 steps already is ~600 instructions; a fully unrolled pointer
 			// word (8 steps) overflows the instruction cache (ncu: stall_no_instruction was the top stall)
 			if (tb >= 32u && tb + 7u <= l2) {
+				if (last_stripe) {
 #pragma unroll AT_WAVE_UNROLL_AFFINE
-				for (uint32_t k = 0; k < 8; ++k) step(tb + k, false);
+					for (uint32_t k = 0; k < 8; ++k) step(tb + k, false, std::true_type());
+				} else {
+#pragma unroll AT_WAVE_UNROLL_AFFINE
+					for (uint32_t k = 0; k < 8; ++k) step(tb + k, false, std::false_type());
+				}
 			} else {
 #pragma unroll 1
-				for (uint32_t k = 0; k < 8; ++k) step(tb + k, true);
+				for (uint32_t k = 0; k < 8; ++k) step(tb + k, true, std::true_type());
 			}
 			if (want_ptr && (tb >> 3) < G) {
 				uint32_t *w = ptr + ((size_t)(stripe * G + (tb >> 3)) * 32 + lane) * R;
