@@ -15,26 +15,26 @@ static uint64_t pipe_slice_cells() { return env_u64("AT_PIPE_SLICE_CELLS", 1ull 
 struct PipeSlice { uint64_t lo = 0, hi = 0; size_t dev = 0; uint64_t tot_ops = 0, tot_cols = 0; bool known = false; };
 
 static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_batch_input *in, uint32_t out_flags,
-                           at_batch_output *out, at_timing *timing, uint64_t total_cells)
+                           at_batch_output *out, at_timing *timing, const std::vector<uint64_t> &prefix)
 {
+	const uint64_t total_cells = prefix[in->n_pairs];
+	const auto t_func = std::chrono::steady_clock::now();
 	const size_t nd = h->devs.size();
-	std::lock_guard<std::mutex> one_at_a_time(h->align_mu);
 	if (h->pipe_ws.size() < nd * AT_PIPE_STREAMS) h->pipe_ws.resize(nd * AT_PIPE_STREAMS, nullptr);
 	std::vector<uint64_t> dcut;
-	cut_by_cells(in, 0, in->n_pairs, nd, dcut);
+	cut_by_prefix(prefix, 0, in->n_pairs, nd, dcut);
 	std::vector<PipeSlice> slices;
 	std::vector<std::vector<size_t>> per_dev(nd);
 	for (size_t d = 0; d < nd; ++d) {
 		if (dcut[d + 1] == dcut[d]) continue;
-		uint64_t cells = 0;
-		for (uint64_t k = dcut[d]; k < dcut[d + 1]; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
+		const uint64_t cells = prefix[dcut[d + 1]] - prefix[dcut[d]];
 		// graduated sub-slices: quarter-size units, grouped 1, 2, 4, 4, 4, ... so that the first kernel starts
 		// early (short first upload) while the bulk runs in full-size sub-slices (fewer kernel tails)
 		size_t units = (size_t)std::max<uint64_t>(1, 4 * cells / pipe_slice_cells());
 		units = std::min<size_t>(units, 256);
 		units = std::min<size_t>(units, (size_t)(dcut[d + 1] - dcut[d]));
 		std::vector<uint64_t> cut;
-		cut_by_cells(in, dcut[d], dcut[d + 1], units, cut);
+		cut_by_prefix(prefix, dcut[d], dcut[d + 1], units, cut);
 		for (size_t u0 = 0, step = 1; u0 < units; u0 += step, step = std::min<size_t>(2 * step, 4)) {
 			const size_t u1 = std::min(units, u0 + step);
 			if (cut[u1] == cut[u0]) continue;
@@ -70,6 +70,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 	const int n_workers = (int)std::min<uint64_t>(AT_PIPE_STREAMS, std::max<uint64_t>(1, env_u64("AT_PIPE_WORKERS", AT_PIPE_STREAMS)));   // diagnosis: fewer workers
 
 	const bool trace = getenv("AT_PIPE_TRACE") != nullptr;      // host timeline of every sub-slice on stderr
+	if (trace) fprintf(stderr, "[at pipe] slicing: %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_func).count());
 	const auto t_origin = std::chrono::steady_clock::now();
 	auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(); };
 	auto worker = [&](size_t d, int w) {
@@ -162,11 +163,17 @@ extern "C" int at_batch_align(at_handle *h, int mode, const at_params *p, const 
                               uint32_t out_flags, at_batch_output *out, at_timing *timing)
 {
 	if (!h || !p || !in || !out || !out->score) return AT_E_ARG;
-	if (int rc = validate_batch(h, mode, p, in)) return rc;
-	uint64_t cells = 0;
-	for (uint64_t k = 0; k < in->n_pairs; ++k) cells += (uint64_t)in->q_len[k] * in->t_len[k];
-	if (cells >= pipe_min_cells() && in->n_pairs >= 16 && !getenv("AT_NO_PIPELINE"))
-		return align_pipelined(h, mode, p, in, out_flags, out, timing, cells);
+	const auto t_entry = std::chrono::steady_clock::now();
+	std::unique_lock<std::mutex> one_at_a_time(h->align_mu);      // the handle's pipeline workspaces serve one call at a time
+	std::vector<uint64_t> &prefix = h->pipe_prefix;
+	if (int rc = validate_batch(h, mode, p, in, &prefix)) return rc;
+	const uint64_t cells = prefix[in->n_pairs];
+	if (cells >= pipe_min_cells() && in->n_pairs >= 16 && !getenv("AT_NO_PIPELINE")) {
+		if (getenv("AT_PIPE_TRACE")) fprintf(stderr, "[at pipe] validation + cell count of %llu pairs: %.2f ms\n", (unsigned long long)in->n_pairs,
+		                                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
+		return align_pipelined(h, mode, p, in, out_flags, out, timing, prefix);
+	}
+	one_at_a_time.unlock();
 	at_batch *b = nullptr;
 	int rc = at_batch_create(h, mode, p, in, out_flags, &b);
 	if (rc) return rc;

@@ -49,6 +49,7 @@ struct at_handle {
 	// at_batch_align's pipeline: one workspace per (device, worker), kept for the life of the handle so
 	// that after the first call a pipelined batch makes no CUDA allocator call at all
 	std::vector<at_batch *> pipe_ws;
+	std::vector<uint64_t> pipe_prefix;     // running cell counts of the batch in hand (kept: no page faults per call)
 	std::mutex align_mu;
 };
 
@@ -662,7 +663,9 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 }
 
 // argument checks shared by at_batch_create and the pipelined at_batch_align; mirrors the reference's own failure modes
-static int validate_batch(at_handle *h, int mode, const at_params *p, const at_batch_input *in)
+// `prefix` (optional): receives the running cell counts, prefix[k] = sum of l1*l2 over pairs < k (n_pairs + 1 entries),
+// so that the one-shot path validates, counts and slices a million-pair batch in one pass
+static int validate_batch(at_handle *h, int mode, const at_params *p, const at_batch_input *in, std::vector<uint64_t> *prefix = nullptr)
 {
 	if (mode < AT_GLOBAL || mode > AT_EDIT) { set_err(h, "bad mode %d", mode); return AT_E_ARG; }
 	if (!in->n_pairs || !in->q || !in->q_off || !in->q_len || !in->t || !in->t_off || !in->t_len) { set_err(h, "align: parameter error"); return AT_E_ARG; }
@@ -670,14 +673,39 @@ static int validate_batch(at_handle *h, int mode, const at_params *p, const at_b
 	if ((in->sites == nullptr) != (in->site_off == nullptr)) return AT_E_ARG;
 	if (in->n_pairs >= (1ull << 31)) return AT_E_ARG;
 	int64_t maxabs = std::max<int64_t>({llabs((long long)p->m), llabs((long long)p->u), llabs((long long)p->o), llabs((long long)p->e), llabs((long long)p->j), 1});
+	const uint64_t max_sum = (uint64_t)(((1ll << 27) - 1) / maxabs);      // (l1 + l2 + 2) * maxabs < 2^27
+	uint64_t *pre = nullptr;
+	if (prefix) { prefix->resize(in->n_pairs + 1); pre = prefix->data(); pre[0] = 0; }
+	uint64_t acc = 0;
 	for (uint64_t k = 0; k < in->n_pairs; ++k) {
 		const uint64_t l1 = in->q_len[k], l2 = in->t_len[k];
 		if (l1 == 0 || l2 == 0) { set_err(h, "pair %llu: empty record", (unsigned long long)k); return AT_E_UNDEF; }
 		if (mode == AT_FIT && l1 > l2) { set_err(h, "pair %llu: first sequence must be shorter than the second to do fitting alignment", (unsigned long long)k); return AT_E_FITLEN; }
 		if (mode == AT_FIT && l2 < 2) { set_err(h, "pair %llu: fit with l2 < 2 is undefined in the reference", (unsigned long long)k); return AT_E_UNDEF; }
-		if ((int64_t)(l1 + l2 + 2) * maxabs >= (1ll << 27)) { set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
+		if (l1 + l2 + 2 > max_sum) { set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
+		acc += l1 * l2;
+		if (pre) pre[k + 1] = acc;
 	}
 	return AT_OK;
+}
+
+// the same slicing rule as cut_by_cells, from running cell counts (binary searches instead of passes over the pairs)
+static void cut_by_prefix(const std::vector<uint64_t> &prefix, uint64_t lo, uint64_t hi, size_t parts, std::vector<uint64_t> &cut)
+{
+	cut.assign(parts + 1, lo);
+	cut[parts] = hi;
+	if (parts <= 1) return;
+	const uint64_t base = prefix[lo], total = prefix[hi] - base;
+	for (size_t d = 1; d < parts; ++d) {
+		// smallest k in [lo, hi) with (prefix[k+1] - base) * parts >= total * d; the slice ends after it
+		uint64_t a = lo, b = hi;
+		while (a < b) {
+			const uint64_t mid = a + (b - a) / 2;
+			if ((unsigned __int128)(prefix[mid + 1] - base) * parts >= (unsigned __int128)total * d) b = mid; else a = mid + 1;
+		}
+		cut[d] = a < hi ? a + 1 : hi;
+	}
+	for (size_t d = 1; d <= parts; ++d) cut[d] = std::max(cut[d], cut[d - 1]);
 }
 
 // contiguous slices of [lo, hi) with (nearly) equal numbers of cells; cut has parts + 1 entries
