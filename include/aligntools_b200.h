@@ -72,7 +72,10 @@ const char *at_version(void);
 typedef struct at_handle at_handle;
 
 /* devices == NULL or n_devices <= 0: use device 0 only.  One host thread + stream per
- * device; pairs are sharded as contiguous slices, no inter-GPU communication. */
+ * device; pairs are sharded as contiguous slices, no inter-GPU communication.
+ * Threading: a handle serves one batch operation at a time (at_batch_align serialises its callers;
+ * at_batch_create / run / fetch of DIFFERENT batches on one handle must not overlap in time).  Use one
+ * handle per host thread for concurrent work; handles are independent. */
 int         at_create(const int *devices, int n_devices, at_handle **out);
 void        at_destroy(at_handle *h);
 const char *at_last_error(const at_handle *h);
