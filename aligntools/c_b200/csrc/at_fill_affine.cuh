@@ -244,6 +244,9 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 			else                         { b0M = ZERO + o8; b0L = NEGV; b0H = ZERO + HM; b0C = V::raw(ST_MID); }                     // :619-624
 			if (lane) { b0M = 0; b0L = 0; b0H = 0; b0C = 0; b0E = 0; }
 			const int cap_r = (!PACKED && last_stripe && lane == (int)(((l1A - 1) % RPP) / R)) ? (int)((l1A - 1) % R) : -1;
+			int hot[R];
+#pragma unroll
+			for (int r = 0; r < R; ++r) hot[r] = r == cap_r ? 1 : 0;
 			T kbest = PACKED ? (T)0 : (T)AT_NEG_INIT;     // below every real key
 			T tbest = 0;
 
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 						}
 					}
 					T Lup = rL, MoUp = rM, Mo = 0, Ln = 0, Hm = 0, code = 0;
+					int rowM = 0, rowL = 0;                        // fit: M, L of the pair's last row
 					const T kold = kbest;
 #pragma unroll
 					for (int r = 0; r < R; ++r) {
@@ -310,18 +314,19 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 						acc[r] = (first ? 0u : acc[r] * 16u) + (uint32_t)(pm | fL) + (uint32_t)fU;
 						if (JUMP) accJ[r] = accJ[r] * 2u + (uint32_t)fJ;
 						if (MODE == MODE_LOCAL) kbest = V::addmax(Mn, crow[r], kbest);
-						if (MODE == MODE_FIT) {
-							if (r == cap_r && j < (int)l2) {                   // column l2 excluded (:677, :684)
-								if ((int)Mn > capM) { capM = (int)Mn; capMj = j; }
-								if ((int)Ln > capL) { capL = (int)Ln; capLj = j; }
-							}
-						}
-						if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) { gH = (int)H; gC = (int)code; } }
+						// fit: the pair's last row is row cap_r of ONE lane: pick its values with a one-hot multiply-add per
+						// row (FMA pipe) instead of compares and selects in every row; the search itself runs once per step
+						if (MODE == MODE_FIT) { rowM += (int)Mn * hot[r]; rowL += (int)Ln * hot[r]; }
+						if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) { gH = (int)H; gC = (int)code; } }   // (cheaper than the one-hot form here)
 						D = Hl[r]; DC = Cl[r];
 						Hl[r] = Hm; Cl[r] = code; Ul[r] = Un; Mol[r] = Mo; if (JUMP) Jl[r] = Jn;
 						Lup = Ln; MoUp = Mo;
 					}
 					sM = Mo; sL = Ln; sH = Hm; sC = code;
+					if (MODE == MODE_FIT && cap_r >= 0 && j < (int)l2) {       // column l2 excluded (:677, :684)
+						if (rowM > capM) { capM = rowM; capMj = j; }
+						if (rowL > capL) { capL = rowL; capLj = j; }
+					}
 					if (MODE == MODE_LOCAL) note_best(kold, kbest, t);
 				} else {
 #pragma unroll

@@ -49,6 +49,10 @@ def main():
     al = A.Aligner()
     if args.glob:
         run(al, "global 150x150 -m1 -u-1 -o-4 -e-1, score+CIGAR", synth.global_short(n_pairs=args.glob), A.OUT_CIGAR)
+    if args.glob:
+        w = synth.global_short(n_pairs=args.glob, l1=150, l2=400)
+        w["mode"] = "fit"; w["params"] = dict(m=1, u=-2, o=-5, e=-1, j=-10, jump=False)
+        run(al, "fit 150x400 (defaults), score+CIGAR", w, A.OUT_CIGAR)
     if args.c3:
         run(al, "C3 fit -s -j -10, 2k x 20k, score+CIGAR", synth.config3_fit_jump(n_pairs=args.c3), A.OUT_CIGAR)
     if args.c4:
