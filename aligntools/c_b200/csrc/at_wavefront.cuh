@@ -537,7 +537,9 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		}
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
 
-		auto step = [&](const uint32_t t, const bool checked) {
+		// `cap`: std::true_type in the pair's last stripe (only there can a lane hold the pair's last row)
+		auto step = [&](const uint32_t t, const bool checked, auto cap) {
+			constexpr bool CAP = decltype(cap)::value;
 			const int j = (int)t - lane;
 			int rV = __shfl_up_sync(0xffffffffu, sV, 1);
 			if (lane == 0) {
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 				}
 				sV = v;
 				if (lane == 31 && !last_stripe) sm.stage[(uint32_t)j & 63u] = sV;
-				if (cap_r >= 0) {                                                 // the pair's last row lives in this lane
+				if (CAP && cap_r >= 0) {                                          // the pair's last row lives in this lane
 					int vc = Vl[0];
 #pragma unroll
 					for (int r = 1; r < R; ++r) if (cap_r == r) vc = Vl[r];
@@ -617,11 +619,16 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
 			}
 			if (tb >= 32u && tb + 15u <= l2) {
+				if (last_stripe) {
 #pragma unroll UNR
-				for (uint32_t k = 0; k < 16; ++k) step(tb + k, false);
+					for (uint32_t k = 0; k < 16; ++k) step(tb + k, false, std::true_type());
+				} else {
+#pragma unroll UNR
+					for (uint32_t k = 0; k < 16; ++k) step(tb + k, false, std::false_type());
+				}
 			} else {
 #pragma unroll 1
-				for (uint32_t k = 0; k < 16; ++k) step(tb + k, true);
+				for (uint32_t k = 0; k < 16; ++k) step(tb + k, true, std::true_type());
 			}
 			if (want_ptr && (tb >> 4) < G) {
 				uint32_t *w = ptr + ((size_t)(stripe * G + (tb >> 4)) * 32 + lane) * R;
