@@ -38,6 +38,7 @@ struct at_device {
 	cudaStream_t stream = nullptr;
 	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // at_batch_align's pipeline streams (created on first use)
 	std::shared_ptr<BigCache> big = std::make_shared<BigCache>();
+	std::shared_ptr<std::mutex> upload_mu = std::make_shared<std::mutex>();   // pipelined path: sub-slices upload their sequences one at a time, in order
 };
 
 struct at_batch;
@@ -437,8 +438,14 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		tl += buf;
 	};
 	uint64_t q_span = 0;
-	if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span))) return rc;
-	if ((rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span))) return rc;
+	{
+		// a pipeline worker waits for the uploads of the sub-slices before its own: the first (small) sub-slice's
+		// sequences are not held up behind a later, larger one sharing the copy engine, and its fill starts early
+		std::unique_lock<std::mutex> one_upload;
+		if (s.workspace) one_upload = std::unique_lock<std::mutex>(*s.dev->upload_mu);
+		if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span))) return rc;
+		if ((rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span))) return rc;
+	}
 	s.d_q2.release(); s.d_t2.release();
 	mark("upload");
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
