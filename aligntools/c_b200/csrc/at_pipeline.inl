@@ -63,6 +63,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 	// finish together and leave the GPU idle while all workers prepare their next sub-slice in lockstep.
 	// The lock is handed on as soon as the fill has completed, so the next fill overlaps the traceback.
 	std::vector<std::mutex> run_mu(nd);
+	std::vector<UploadGate> gate(nd);          // uploads of a device's sub-slices go one at a time, in pair order
 	std::vector<std::atomic<size_t>> next(nd);
 	for (auto &x : next) x = 0;
 	struct Acc { double fill = 0, tb = 0, dev = 0, domk = 0; uint64_t domc = 0, launches = 0, ptr = 0; };
@@ -85,7 +86,8 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 		b->traceback = mode != AT_EDIT && (out_flags & (AT_OUT_CIGAR | AT_OUT_ALN));
 		for (;;) {
 			const size_t k = next[d].fetch_add(1);
-			if (k >= per_dev[d].size() || failed.load()) break;
+			if (k >= per_dev[d].size()) break;
+			if (failed.load()) { gate[d].pass(k); break; }      // a later sub-slice may already wait for this turn
 			const size_t si = per_dev[d][k];
 			PipeSlice &sl = slices[si];
 			at_batch_input sub = *in;
@@ -96,12 +98,17 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 			b->n = sub.n_pairs;
 			Shard &s = b->shards[0];
 			s.dev = &dv; s.stream = dv.pipe[w]; s.workspace = true; s.p0 = 0; s.p1 = sub.n_pairs; s.n = (uint32_t)sub.n_pairs; s.out_base = sl.lo;
+			s.gate = &gate[d]; s.gate_turn = k;
 			const double t_a = now_ms();
 			int rc = setup_shard(b, s, &sub);
+			gate[d].pass(k);                        // also when the set-up returned before its upload
+			s.gate = nullptr;
 			const double t_b = now_ms();
+			double t_lock = 0, t_hand = 0;
 			if (!rc) {
 				std::unique_lock<std::mutex> own(run_mu[d]);
-				const std::function<void()> hand_on = [&] { if (own.owns_lock()) own.unlock(); };
+				t_lock = now_ms();
+				const std::function<void()> hand_on = [&] { if (own.owns_lock()) { own.unlock(); t_hand = now_ms(); } };
 				rc = run_shard(b, s, &hand_on);
 			}
 			const double t_c = now_ms();
@@ -122,8 +129,8 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 					rc = AT_E_NOSPACE;
 				} else rc = fetch_shard(b, s, out, want_cig, want_aln, base_ops, base_cols);
 			}
-			if (trace) fprintf(stderr, "[at pipe] dev %zu stream %d slice %zu pairs %llu: setup %.2f-%.2f run -%.2f fetch -%.2f ms (fill %.2f tb %.2f)\n",
-			                   d, w, si, (unsigned long long)sub.n_pairs, t_a, t_b, t_c, now_ms(), s.fill_ms, s.tb_ms);
+			if (trace) fprintf(stderr, "[at pipe] dev %zu stream %d slice %zu pairs %llu: setup %.2f-%.2f SMs %.2f-%.2f run -%.2f fetch -%.2f ms (fill %.2f tb %.2f)\n",
+			                   d, w, si, (unsigned long long)sub.n_pairs, t_a, t_b, t_lock, t_hand, t_c, now_ms(), s.fill_ms, s.tb_ms);
 			a.fill += s.fill_ms; a.tb += s.tb_ms; a.dev += s.dev_ms; a.launches += s.launches; a.ptr += traceback ? s.ptr_bytes : 0;
 			if (s.domk_cells > a.domc) { a.domc = s.domk_cells; a.domk = s.domk_ms; }
 			if (rc) { std::lock_guard<std::mutex> lk(mu); failed = rc; cv.notify_all(); break; }

@@ -38,7 +38,6 @@ struct at_device {
 	cudaStream_t stream = nullptr;
 	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // at_batch_align's pipeline streams (created on first use)
 	std::shared_ptr<BigCache> big = std::make_shared<BigCache>();
-	std::shared_ptr<std::mutex> upload_mu = std::make_shared<std::mutex>();   // pipelined path: sub-slices upload their sequences one at a time, in order
 };
 
 struct at_batch;
@@ -176,8 +175,16 @@ struct Chunk {
 	uint64_t bnd_elems = 0, prog_words = 0;
 	DevBuf<uint64_t> d_ops_off, d_cols_off, d_scratch_off;
 	std::vector<uint64_t> h_scratch_off; uint64_t scratch_words = 0;
-	DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_aln1, d_aln2;
+	DevBuf<uint32_t> d_cigar; DevBuf<uint8_t> d_aln1, d_aln2;   // exact-size outputs of this chunk ...
+	uint32_t *cigar = nullptr; uint8_t *aln1 = nullptr, *aln2 = nullptr;   // ... or the workspace's grow-only buffers (pipelined path); what fetch reads
 	uint64_t tot_ops = 0, tot_cols = 0;
+};
+
+// Sub-slices of one device take turns (in pair order) on the host->device copy of their sequences.
+struct UploadGate {
+	std::mutex mu; std::condition_variable cv; uint64_t turn = 0;
+	void wait_for(uint64_t k) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return turn >= k; }); }
+	void pass(uint64_t k) { std::lock_guard<std::mutex> lk(mu); if (turn < k + 1) { turn = k + 1; cv.notify_all(); } }    // idempotent
 };
 
 struct Shard {
@@ -190,11 +197,13 @@ struct Shard {
 	DevBuf<uint64_t> d_q_off, d_t_off, d_site_off;
 	DevBuf<uint32_t> d_q_len, d_t_len, d_end_i, d_end_j, d_beg_i, d_beg_j, d_n_ops, d_n_cols, d_counter;
 	DevBuf<int32_t> d_score, d_sites;
+	DevBuf<uint32_t> ws_cigar; DevBuf<uint8_t> ws_aln1, ws_aln2;     // pipeline workspace: outputs of the sub-slice, sized by their upper bound
 	DevBuf<uint32_t> d_ptr, d_scratch, d_prog; DevBuf<uint8_t> d_bnd, d_scan_tmp; DevBuf<int32_t> d_chain;
 	DevBuf<uint8_t> d_symmap; DevBuf<uint32_t> d_symset;
 	bool prof = false; uint32_t syms = 0;      // query-profile variant of K1: the targets use <= 4 distinct bytes
 	bool bits = false;                         // bit-parallel edit distance: `-u 1` and reads of <= 8 distinct bytes
 	BufCache cache;                            // released device blocks, reused by this shard's next allocations
+	struct UploadGate *gate = nullptr; uint64_t gate_turn = 0;   // pipelined path: sub-slices upload their sequences one at a time, in pair order
 	bool workspace = false;                    // pipeline workspace: reused for many sub-slices, buffers get head-room
 	std::vector<uint8_t> h_rclass;
 	std::vector<Chunk> chunks;
@@ -318,6 +327,7 @@ static void free_shard(Shard &s)
 	s.d_q_off.release(); s.d_t_off.release(); s.d_site_off.release();
 	s.d_q_len.release(); s.d_t_len.release(); s.d_end_i.release(); s.d_end_j.release(); s.d_beg_i.release();
 	s.d_beg_j.release(); s.d_n_ops.release(); s.d_n_cols.release(); s.d_counter.release();
+	s.ws_cigar.release(); s.ws_aln1.release(); s.ws_aln2.release();
 	s.d_score.release(); s.d_sites.release(); s.d_ptr.release(); s.d_scratch.release(); s.d_bnd.release(); s.d_scan_tmp.release();
 	s.d_prog.release(); s.d_chain.release(); s.d_symmap.release(); s.d_symset.release();
 	release_chunks(s);
@@ -441,10 +451,11 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	{
 		// a pipeline worker waits for the uploads of the sub-slices before its own: the first (small) sub-slice's
 		// sequences are not held up behind a later, larger one sharing the copy engine, and its fill starts early
-		std::unique_lock<std::mutex> one_upload;
-		if (s.workspace) one_upload = std::unique_lock<std::mutex>(*s.dev->upload_mu);
-		if ((rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span))) return rc;
-		if ((rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span))) return rc;
+		if (s.gate) s.gate->wait_for(s.gate_turn);
+		rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span);
+		if (!rc) rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span);
+		if (s.gate) s.gate->pass(s.gate_turn);
+		if (rc) return rc;
 	}
 	s.d_q2.release(); s.d_t2.release();
 	mark("upload");
@@ -683,15 +694,46 @@ static int validate_batch(at_handle *h, int mode, const at_params *p, const at_b
 	const uint64_t max_sum = (uint64_t)(((1ll << 27) - 1) / maxabs);      // (l1 + l2 + 2) * maxabs < 2^27
 	uint64_t *pre = nullptr;
 	if (prefix) { prefix->resize(in->n_pairs + 1); pre = prefix->data(); pre[0] = 0; }
-	uint64_t acc = 0;
-	for (uint64_t k = 0; k < in->n_pairs; ++k) {
-		const uint64_t l1 = in->q_len[k], l2 = in->t_len[k];
-		if (l1 == 0 || l2 == 0) { set_err(h, "pair %llu: empty record", (unsigned long long)k); return AT_E_UNDEF; }
-		if (mode == AT_FIT && l1 > l2) { set_err(h, "pair %llu: first sequence must be shorter than the second to do fitting alignment", (unsigned long long)k); return AT_E_FITLEN; }
-		if (mode == AT_FIT && l2 < 2) { set_err(h, "pair %llu: fit with l2 < 2 is undefined in the reference", (unsigned long long)k); return AT_E_UNDEF; }
-		if (l1 + l2 + 2 > max_sum) { set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
-		acc += l1 * l2;
-		if (pre) pre[k + 1] = acc;
+	// one pair's checks, in the reference's order of failure; `report` false = only say whether it fails
+	auto check = [&](uint64_t k, uint64_t l1, uint64_t l2, bool report) -> int {
+		if (l1 == 0 || l2 == 0) { if (report) set_err(h, "pair %llu: empty record", (unsigned long long)k); return AT_E_UNDEF; }
+		if (mode == AT_FIT && l1 > l2) { if (report) set_err(h, "pair %llu: first sequence must be shorter than the second to do fitting alignment", (unsigned long long)k); return AT_E_FITLEN; }
+		if (mode == AT_FIT && l2 < 2) { if (report) set_err(h, "pair %llu: fit with l2 < 2 is undefined in the reference", (unsigned long long)k); return AT_E_UNDEF; }
+		if (l1 + l2 + 2 > max_sum) { if (report) set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
+		return AT_OK;
+	};
+	// ranges of pairs: checks and the range's cell total in one pass (a few host threads on a large batch),
+	// the running cell counts in a second pass once every range knows its base
+	const uint64_t n = in->n_pairs;
+	const size_t parts = n >= (1u << 17) ? 4 : 1;
+	std::vector<uint64_t> lo(parts + 1), sum(parts, 0), bad(parts, UINT64_MAX);
+	for (size_t r = 0; r <= parts; ++r) lo[r] = n * r / parts;
+	auto pass1 = [&](size_t r) {
+		uint64_t acc = 0;
+		for (uint64_t k = lo[r]; k < lo[r + 1]; ++k) {
+			const uint64_t l1 = in->q_len[k], l2 = in->t_len[k];
+			if (check(k, l1, l2, false)) { bad[r] = k; break; }
+			acc += l1 * l2;
+		}
+		sum[r] = acc;
+	};
+	auto pass2 = [&](size_t r, uint64_t acc) {
+		for (uint64_t k = lo[r]; k < lo[r + 1]; ++k) { acc += (uint64_t)in->q_len[k] * in->t_len[k]; pre[k + 1] = acc; }
+	};
+	auto each_range = [&](const std::function<void(size_t)> &fn) {
+		if (parts == 1) { fn(0); return; }
+		std::vector<std::thread> th;
+		for (size_t r = 1; r < parts; ++r) th.emplace_back(fn, r);
+		fn(0);
+		for (auto &t : th) t.join();
+	};
+	each_range(pass1);
+	for (size_t r = 0; r < parts; ++r)
+		if (bad[r] != UINT64_MAX) return check(bad[r], in->q_len[bad[r]], in->t_len[bad[r]], true);   // the first failing pair, as a serial scan would report
+	if (pre) {
+		std::vector<uint64_t> base(parts, 0);
+		for (size_t r = 1; r < parts; ++r) base[r] = base[r - 1] + sum[r - 1];
+		each_range([&](size_t r) { pass2(r, base[r]); });
 	}
 	return AT_OK;
 }
@@ -826,9 +868,10 @@ static wave_fn wave_kernel(int mode, bool jump, int R, bool prof)
 
 struct CastU64 { __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; } };
 
-// `fills_done` (optional) is called once, right after the fill kernels of the shard's LAST chunk have
-// completed on the device: the pipelined one-shot path hands the SMs to the next sub-slice there, so
-// its fill overlaps this sub-slice's traceback kernels and host round trips.
+// `fills_done` (optional) is called once, when the next sub-slice of the pipelined one-shot path may
+// launch its fill: after this shard's last traceback kernel has been enqueued (score-only: after its
+// fills completed), so the device runs fill, traceback, next fill back to back while this shard's
+// D2H copies and host work overlap the next fill.
 static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_done = nullptr)
 {
 	at_handle *h = b->h;
@@ -837,6 +880,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 	tl_stream = st;
 	tl_cache = &s.cache; tl_big = s.dev->big.get();
 	const bool jump = b->mode == AT_FIT && b->prm.jump;
+	static const bool tb_overlap = getenv("AT_PIPE_TB_OVERLAP") != nullptr;
 	s.fill_ms = s.tb_ms = s.dev_ms = s.domk_ms = 0; s.domk_cells = 0; s.launches = 0;
 	// dominant (most cells) fill launch of the whole shard -> per-launch timing for the roofline
 	int dom_chunk = -1, dom_launch = -1; uint64_t dom_cells = 0;
@@ -866,9 +910,9 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			int occ = 0;
 			CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * warps, dyn_smem));
 			if (occ < 1) { set_err(h, "fill kernel (mode %d, R %d) cannot be resident: not an sm_100 build?", b->mode, l.r); return AT_E_CUDA; }
-			// pipelined one-shot path: leave shared memory for the helper kernels of the neighbouring sub-slices
-			// (a K1 grid at full occupancy fills an SM's shared memory; nothing else could run beside it)
-			if (s.workspace && l.kind != LK_WAVE && l.kind != LK_BITS && occ > 4 && !getenv("AT_PIPE_FULL_OCC")) occ = 4;
+			// AT_PIPE_TB_OVERLAP (older scheme, kept for A/B runs): traceback kernels run beside the next sub-slice's
+			// fill, which must then leave them shared memory and registers (a K1 grid at full occupancy fills an SM)
+			if (tb_overlap && s.workspace && l.kind != LK_WAVE && l.kind != LK_BITS && occ > 4) occ = 4;
 			int blocks = (int)std::min<uint64_t>((uint64_t)s.dev->sm_count * occ, (l.n_jobs() + warps - 1) / warps);
 			if (blocks < 1) blocks = 1;
 			const bool dom = (int)ci == dom_chunk && (int)li == dom_launch;
@@ -904,7 +948,12 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			s.launches++;
 		}
 		CU(h, cudaEventRecord(e_fill, st));
-		if (fills_done && ci + 1 == s.chunks.size()) { CU(h, cudaEventSynchronize(e_fill)); (*fills_done)(); }
+		const bool last_chunk = ci + 1 == s.chunks.size();
+		// pipelined one-shot path: the SMs go to the next sub-slice once this one's traceback kernels are in the
+		// queue ahead of its fill -- the fill runs at full occupancy and the (short) traceback is not squeezed
+		// beside it; copies and host round trips still overlap the neighbours' fills
+		const bool tb_first = fills_done && last_chunk && b->traceback && !tb_overlap;
+		if (fills_done && last_chunk && !tb_first) { CU(h, cudaEventSynchronize(e_fill)); (*fills_done)(); }
 		if (b->traceback) {
 			TraceArgs ta;
 			ta.q = s.d_q.p; ta.q_off = s.d_q_off.p; ta.q_len = s.d_q_len.p;
@@ -919,7 +968,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			ta.mode = b->mode; ta.jump = jump ? 1 : 0;
 			ta.lookahead = nc < 32768u ? 1 : 0;       // with many short walks the chase is throughput-bound and the prefetches only add traffic
 			const int walk_blocks = ta.lookahead ? (int)(((uint64_t)nc * 32 + 127) / 128) : (int)((nc + 127) / 128);   // one walker per warp | per thread
-			if (s.workspace) at_traceback_walk<true><<<walk_blocks, 128, 0, st>>>(ta);
+			if (s.workspace && tb_overlap) at_traceback_walk<true><<<walk_blocks, 128, 0, st>>>(ta);
 			else at_traceback_walk<false><<<walk_blocks, 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
@@ -939,20 +988,47 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_ops, c.d_ops_off.p + 1, (int)nc, st));
 				CU(h, cub::DeviceScan::InclusiveSum(s.d_scan_tmp.p, tmp_bytes, it_cols, c.d_cols_off.p + 1, (int)nc, st));
 			}
-			uint64_t tot[2] = {0, 0};
-			CU(h, cudaMemcpyAsync(&tot[0], c.d_ops_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-			CU(h, cudaMemcpyAsync(&tot[1], c.d_cols_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-			CU(h, cudaStreamSynchronize(st));
-			c.tot_ops = tot[0]; c.tot_cols = tot[1];
 			const bool want_cig = b->out_flags & AT_OUT_CIGAR, want_aln = b->out_flags & AT_OUT_ALN;
-			if (want_cig) { if (c.d_cigar.alloc(c.tot_ops + 1) != cudaSuccess) { set_err(h, "cigar buffer"); return AT_E_NOMEM; } }
-			if (want_aln) { if (c.d_aln1.alloc(c.tot_cols + 1) != cudaSuccess || c.d_aln2.alloc(c.tot_cols + 1) != cudaSuccess) { set_err(h, "alignment buffer"); return AT_E_NOMEM; } }
-			ta.cigar = want_cig ? c.d_cigar.p : nullptr;
-			ta.aln1 = want_aln ? c.d_aln1.p : nullptr; ta.aln2 = want_aln ? c.d_aln2.p : nullptr;
-			if (s.workspace) at_traceback_emit<true><<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
+			auto out_buffers = [&](uint64_t ops, uint64_t cols) -> int {
+				// tb_first: the workspace's own buffers, kept across sub-slices and calls (grow-only) -- upper-bound sized
+				// blocks are too large to go through the allocator in the steady state
+				DevBuf<uint32_t> &cg = tb_first ? s.ws_cigar : c.d_cigar;
+				DevBuf<uint8_t> &a1 = tb_first ? s.ws_aln1 : c.d_aln1, &a2 = tb_first ? s.ws_aln2 : c.d_aln2;
+				if (want_cig) { if (cg.alloc(ops + 1) != cudaSuccess) { set_err(h, "cigar buffer"); return AT_E_NOMEM; } }
+				if (want_aln) { if (a1.alloc(cols + 1) != cudaSuccess || a2.alloc(cols + 1) != cudaSuccess) { set_err(h, "alignment buffer"); return AT_E_NOMEM; } }
+				ta.cigar = c.cigar = want_cig ? cg.p : nullptr;
+				ta.aln1 = c.aln1 = want_aln ? a1.p : nullptr; ta.aln2 = c.aln2 = want_aln ? a2.p : nullptr;
+				return AT_OK;
+			};
+			uint64_t tot[2] = {0, 0};
+			if (tb_first) {
+				// no host round trip between the walk and the emit: the outputs are sized by their upper bound
+				// (an alignment has at most l1 + l2 columns; the workspace keeps the buffers), the totals follow later
+				// (rounded up generously: sub-slices differ by a few pairs, and a request just above every cached
+				// block would go to the CUDA allocator, which waits for the fills already in the queue)
+				const uint64_t cap = (c.scratch_words + c.scratch_words / 8 + (1u << 22)) & ~(uint64_t)((1u << 22) - 1);
+				if (int rc = out_buffers(cap, cap)) return rc;
+			} else {
+				CU(h, cudaMemcpyAsync(&tot[0], c.d_ops_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+				CU(h, cudaMemcpyAsync(&tot[1], c.d_cols_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+				CU(h, cudaStreamSynchronize(st));
+				if (int rc = out_buffers(tot[0], tot[1])) return rc;
+			}
+			if (s.workspace && tb_overlap) at_traceback_emit<true><<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
 			else at_traceback_emit<false><<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
 			CU(h, cudaGetLastError());
 			s.launches++;
+			if (tb_first) {
+				// the next fill is launched once this one has COMPLETED: launched earlier it would take the SMs
+				// as this fill's blocks retire, and this sub-slice's traceback (and its workspace) would wait a whole
+				// fill behind it -- the workers then fall into lockstep
+				CU(h, cudaEventSynchronize(e_fill));
+				(*fills_done)();
+				CU(h, cudaMemcpyAsync(&tot[0], c.d_ops_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+				CU(h, cudaMemcpyAsync(&tot[1], c.d_cols_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+				CU(h, cudaStreamSynchronize(st));
+			}
+			c.tot_ops = tot[0]; c.tot_cols = tot[1];
 		}
 		CU(h, cudaEventRecord(e_tb, st));
 		CU(h, cudaStreamSynchronize(st));
@@ -1018,13 +1094,13 @@ static int fetch_shard(at_batch *b, Shard &s, at_batch_output *out, bool want_ci
 		const uint32_t nc = c.k1 - c.k0;
 		if (want_cig) {
 			CU(h, cudaMemcpyAsync(out->cigar_off + ob + c.k0, c.d_ops_off.p, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-			if (c.tot_ops) CU(h, cudaMemcpyAsync(out->cigar + base_ops, c.d_cigar.p, c.tot_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+			if (c.tot_ops) CU(h, cudaMemcpyAsync(out->cigar + base_ops, c.cigar, c.tot_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
 		}
 		if (want_aln) {
 			CU(h, cudaMemcpyAsync(out->aln_off + ob + c.k0, c.d_cols_off.p, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 			if (c.tot_cols) {
-				CU(h, cudaMemcpyAsync(out->aln1 + base_cols, c.d_aln1.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
-				CU(h, cudaMemcpyAsync(out->aln2 + base_cols, c.d_aln2.p, c.tot_cols, cudaMemcpyDeviceToHost, st));
+				CU(h, cudaMemcpyAsync(out->aln1 + base_cols, c.aln1, c.tot_cols, cudaMemcpyDeviceToHost, st));
+				CU(h, cudaMemcpyAsync(out->aln2 + base_cols, c.aln2, c.tot_cols, cudaMemcpyDeviceToHost, st));
 			}
 		}
 		CU(h, cudaStreamSynchronize(st));

@@ -207,6 +207,27 @@ def test_error_codes(A, aligner):
     assert e.value.rc == -7
 
 
+def test_error_codes_large_batch(A, aligner):
+    """Batches of 2^17 pairs and more are validated by several host threads over ranges of pairs;
+    the error reported must still be the FIRST failing pair's, as a serial scan finds it."""
+    n = (1 << 17) + 11
+    q = np.frombuffer(b"ACGT" * 2, np.uint8).copy()
+    q_off = np.zeros(n, np.uint64); t_off = np.zeros(n, np.uint64)
+    q_len = np.full(n, 3, np.uint32); t_len = np.full(n, 5, np.uint32)
+    q_len[n - 7] = 0                           # last range: empty record (AT_E_UNDEF)
+    q_len[n // 2 + 3] = 6                      # third range: l1 > l2 (AT_E_FITLEN) -- the first in pair order
+    with pytest.raises(A.AtError) as e:
+        aligner.align_arrays("fit", A.Opt(), q, q_off, q_len, q, t_off, t_len, out_flags=0)
+    assert e.value.rc == -4 and ("pair %d:" % (n // 2 + 3)) in str(e.value)
+    q_len[5] = 0                               # first range
+    with pytest.raises(A.AtError) as e:
+        aligner.align_arrays("fit", A.Opt(), q, q_off, q_len, q, t_off, t_len, out_flags=0)
+    assert e.value.rc == -7 and "pair 5:" in str(e.value)
+    q_len[:] = 3                               # and a clean batch of that size goes through (global 3 x 5, identical pairs)
+    res = aligner.align_arrays("global", A.Opt(), q, q_off, q_len, q, t_off, t_len, out_flags=0)
+    assert (res.score == res.score[0]).all()
+
+
 def test_reference_named_operators(A):
     """Single-pair operators with the reference's names (README examples)."""
     sc, r1, r2 = A.align_local_affine(b"PLEASANTLY", b"MEANLY", A.Opt(m=2, u=-2, o=-5, e=-2))
