@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--one-shot", type=float, default=0.3, help="share of rounds that go through the pipelined at_batch_align")
     args = ap.parse_args()
     rng = random.Random(args.seed)
     al = A.Aligner()
@@ -77,10 +78,13 @@ def main():
         p = oracle.Params(prm["m"], prm["u"], prm["o"], prm["e"], prm["j"], prm["jump"])
         ref = oracle.port_batch(md, p, qb, qo, ql, tb, to, tl, sites, site_off, want_aln=(md != "edit"), want_ops=(md != "edit"), threads=16)
         flags = 0 if md == "edit" else 3
-        if rng.random() < 0.3:
+        if rng.random() < args.one_shot:
             os.environ["AT_PIPE_MIN_CELLS"] = "1"; os.environ["AT_PIPE_SLICE_CELLS"] = str(rng.choice([20000, 300000, 5000000]))
+            if rng.random() < 0.3: os.environ["AT_PTR_BUDGET_MB"] = "48"       # several chunks per sub-slice
+            else: os.environ.pop("AT_PTR_BUDGET_MB", None)
             res = al.align_arrays(md, opt, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off, out_flags=flags)
         else:
+            os.environ.pop("AT_PTR_BUDGET_MB", None)
             b = al.batch(md, opt, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off, out_flags=flags)
             b.run(); res = b.fetch(); b.free()
         ok = np.array_equal(res.score.astype(np.int64), ref.score)
