@@ -966,7 +966,9 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			ta.scratch = s.d_scratch.p; ta.scratch_off = c.d_scratch_off.p;
 			ta.cigar = nullptr; ta.aln1 = nullptr; ta.aln2 = nullptr;
 			ta.mode = b->mode; ta.jump = jump ? 1 : 0;
-			ta.lookahead = nc < 32768u ? 1 : 0;       // with many short walks the chase is throughput-bound and the prefetches only add traffic
+			// few long walks: one walker per warp, prefetching ahead; with many walks, or short ones (a few hundred
+			// steps: nothing to prefetch far ahead of), the chase is throughput-bound and the prefetches only add traffic
+			ta.lookahead = nc < 32768u && c.scratch_words / nc >= 2048 ? 1 : 0;
 			const int walk_blocks = ta.lookahead ? (int)(((uint64_t)nc * 32 + 127) / 128) : (int)((nc + 127) / 128);   // one walker per warp | per thread
 			if (s.workspace && tb_overlap) at_traceback_walk<true><<<walk_blocks, 128, 0, st>>>(ta);
 			else at_traceback_walk<false><<<walk_blocks, 128, 0, st>>>(ta);
