@@ -61,7 +61,8 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 	std::atomic<int> failed{0};
 	// one sub-slice's FILL at a time owns a device's SMs: concurrent persistent fills would share them,
 	// finish together and leave the GPU idle while all workers prepare their next sub-slice in lockstep.
-	// The lock is handed on as soon as the fill has completed, so the next fill overlaps the traceback.
+	// The lock is handed on when the fill has completed and the sub-slice's traceback kernels are already in
+	// the queue behind it: the device runs fill, traceback, next fill back to back (run_shard, `fills_done`).
 	std::vector<std::mutex> run_mu(nd);
 	std::vector<UploadGate> gate(nd);          // uploads of a device's sub-slices go one at a time, in pair order
 	std::vector<std::atomic<size_t>> next(nd);
