@@ -35,7 +35,8 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 		units = std::min<size_t>(units, (size_t)(dcut[d + 1] - dcut[d]));
 		std::vector<uint64_t> cut;
 		cut_by_prefix(prefix, dcut[d], dcut[d + 1], units, cut);
-		for (size_t u0 = 0, step = 1; u0 < units; u0 += step, step = std::min<size_t>(2 * step, 4)) {
+		const size_t max_group = (size_t)std::max<uint64_t>(1, env_u64("AT_PIPE_MAX_GROUP", 4));
+		for (size_t u0 = 0, step = 1; u0 < units; u0 += step, step = std::min<size_t>(2 * step, max_group)) {
 			const size_t u1 = std::min(units, u0 + step);
 			if (cut[u1] == cut[u0]) continue;
 			PipeSlice sl; sl.lo = cut[u0]; sl.hi = cut[u1]; sl.dev = d;
