@@ -109,6 +109,16 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 	typedef typename V::T T;
 	static_assert(!PACKED || (MODE == MODE_LOCAL && !JUMP), "packed lanes: local mode");
 	constexpr uint32_t SPW = V::STEPS_PER_WORD;
+	// TAG (packed lanes + query profile): the argmax of every max rides in the three spare low bits of the
+	// x8-scaled values instead of being derived with subtract + min pairs.  Candidates carry a tie-break tag
+	// into the max (one VIADDMNMX each), one LOP3 per propagated value drops it again:
+	//   H' = clean | code of the winner (L 2, M 1, U 0: L wins ties, then M -- the reference's order)
+	//   L' = clean | 2,  U' = clean,  Mo' = M + o + 2
+	//   Ln_t = max(L' + e + 4, Mo')      low bits 6: extended (ties included, :456), 2: opened
+	//   Un_t = max(U' + e, Mo')          low bits 0: extended, 2: opened (ties included, :460)
+	//   Mn_t = max(H'diag + s + 1, ZERO) low bits 0: HOME (0.0 strictly greater, :825), else diagonal code + 1
+	// The pointer nibble is the complement of (Mn_t & 3) | (Ln_t & 4) | (Un_t & 2) << 2; words are inverted at the store.
+	constexpr bool TAG = PACKED && PROF;
 	constexpr int RPP = 32 * R;
 	constexpr int LS = k1_lane_stride(R), NC = prof_combs(PACKED);
 	constexpr uint32_t COMB_BYTES = 32u * LS * 4u;             // one comb's slice of the profile
@@ -130,6 +140,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 	const uint32_t mu8 = (uint32_t)(8 * (m >= u ? m - u : u - m));     // per half; < 1 << CSHIFT (host-checked)
 	const int nsg = m >= u ? -1 : 1;                                    // M = (H+m) - penalty  (or + when u > m)
 	const T ZERO = V::value(0);
+	const T e8h4 = V::delta_h(e) + V::raw(4), o8p1 = o8 + V::raw(1);              // TAG: extension tag of L, M' (low bits 1) -> Mo' (low bits 2)
 	const T NEGV = PACKED ? ZERO : (T)AT_NEG;                           // -inf stand-in (int32 lanes only)
 	const bool want_ptr = a.want_ptr != 0;
 
@@ -201,7 +212,9 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					const uint32_t cb = ri < l1B ? ((uint32_t)qB[ri] << 8) : 0x0002u;
 					ac[r] = ca | (cb << 16);
 					// running-max key offset: 7 - r for real rows; -0x8000 sinks padded rows below every real key
-					crow[r] = (T)((ri < l1A ? (uint32_t)(7 - r) : 0x8000u) | ((ri < l1B ? (uint32_t)(7 - r) : 0x8000u) << 16));
+					// (TAG: the key is built from M' = M | 1, so the offsets are one less -- per half, two's complement)
+					const uint32_t ka = (ri < l1A ? (uint32_t)(7 - r) : 0x8000u) - (TAG ? 1u : 0u), kb = (ri < l1B ? (uint32_t)(7 - r) : 0x8000u) - (TAG ? 1u : 0u);
+					crow[r] = (T)((ka & 0xffffu) | ((kb & 0xffffu) << 16));
 				} else {
 					ac[r] = ri < l1A ? ((uint32_t)qA[ri] << 16) : 0x4u;
 					crow[r] = (T)(ri < l1A ? 7 - r : -(1 << 28));
@@ -210,6 +223,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 				if (MODE == MODE_GLOBAL)     { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = V::value(o + e * i) + HM; Cl[r] = V::raw(ST_LOW); }   // :432-436
 				else if (MODE == MODE_LOCAL) { Mol[r] = ZERO + o8; Ul[r] = ZERO; Hl[r] = ZERO + HM; Cl[r] = V::raw(ST_LOW); }             // calloc zeros
 				else                         { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = NEGV; Cl[r] = V::raw(ST_MID); }                       // :612-617
+				if (TAG) { Mol[r] = ZERO + o8 + V::raw(2); Hl[r] = ZERO + V::raw(2); }                                                    // Mo', H' = 0 | LOW
 				Jl[r] = NEGV; acc[r] = 0; accJ[r] = 0;
 				if (PROF) {     // this lane's rows of the query profile: 8*s(read symbol, target symbol of code c)
 					const uint32_t qa = ri < l1A ? (uint32_t)qA[ri] : 0x100u, qb = (PACKED && ri < l1B) ? (uint32_t)qB[ri] : 0x100u;
@@ -221,27 +235,32 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					}
 #pragma unroll
 					for (int c = 0; c < NC; ++c)
-						prof[(c * 32 + lane) * LS + r] = PACKED ? (uint32_t)(sa[c >> 2] + sb[c & 3] * 65536) : (uint32_t)sa[c];
+						prof[(c * 32 + lane) * LS + r] = TAG ? (((uint32_t)(sa[c >> 2] + 1) & 0xffffu) | ((uint32_t)(sb[c & 3] + 1) << 16))   // 8 s + 1 per half, two's complement (VIADDMNMX.U16x2 adds per half)
+						                                 : PACKED ? (uint32_t)(sa[c >> 2] + sb[c & 3] * 65536) : (uint32_t)sa[c];
 				}
 			}
 			if (PROF) __syncwarp();
 			T sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
 			T sL = MODE == MODE_GLOBAL ? V::value(o + e * (int)(row0 + R)) : (MODE == MODE_LOCAL ? ZERO : NEGV);
+			if (TAG) sL = ZERO + V::raw(2);
 			T pH, pC;      // H(row0, 0) + m and its code
 			if (row0 == 0) {
 				if (MODE == MODE_GLOBAL)     { pH = V::value(o < 0 ? 0 : o) + HM; pC = V::raw(o < 0 ? ST_MID : ST_LOW); }   // max5(L=o, M=0, U=o)
 				else if (MODE == MODE_LOCAL) { pH = ZERO + HM; pC = V::raw(ST_LOW); }
 				else                         { pH = ZERO + HM; pC = V::raw(ST_MID); }                                       // M[0][0]=U[0][0]=0
+				if (TAG) pH = ZERO + V::raw(2);
 			} else {
 				if (MODE == MODE_GLOBAL)     { pH = V::value(o + e * (int)row0) + HM; pC = V::raw(ST_LOW); }
 				else if (MODE == MODE_LOCAL) { pH = ZERO + HM; pC = V::raw(ST_LOW); }
 				else                         { pH = NEGV; pC = V::raw(ST_MID); }
+				if (TAG) pH = ZERO + V::raw(2);
 			}
 			// matrix row 0 as lane 0 sees it (zero in every other lane: x = neighbour * nz + b0)
 			T b0M, b0L, b0H, b0C, b0E = 0;
 			if (MODE == MODE_GLOBAL)     { b0M = NEGV; b0L = NEGV; b0H = V::value(o) + HM; b0C = V::raw(ST_UPP); b0E = e8; }         // :437-441, U[0][j] = o + e j
 			else if (MODE == MODE_LOCAL) { b0M = ZERO + o8; b0L = ZERO; b0H = ZERO + HM; b0C = V::raw(ST_LOW); }
 			else                         { b0M = ZERO + o8; b0L = NEGV; b0H = ZERO + HM; b0C = V::raw(ST_MID); }                     // :619-624
+			if (TAG) { b0M = ZERO + o8 + V::raw(2); b0L = ZERO + V::raw(2); b0H = ZERO + V::raw(2); }     // Mo', L', H' of matrix row 0
 			if (lane) { b0M = 0; b0L = 0; b0H = 0; b0C = 0; b0E = 0; }
 			const int cap_r = (!PACKED && last_stripe && lane == (int)(((l1A - 1) % RPP) / R)) ? (int)((l1A - 1) % R) : -1;
 			int hot[R];
@@ -262,7 +281,8 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 				T rM = __shfl_up_sync(0xffffffffu, sM, 1) * nz + b0M;
 				T rL = __shfl_up_sync(0xffffffffu, sL, 1) * nz + b0L;
 				T rH = __shfl_up_sync(0xffffffffu, sH, 1) * nz + b0H;
-				T rC = __shfl_up_sync(0xffffffffu, sC, 1) * nz + b0C;
+				T rC = 0;
+				if (!TAG) rC = __shfl_up_sync(0xffffffffu, sC, 1) * nz + b0C;
 				if (MODE == MODE_GLOBAL) rH += b0E * (T)t;
 				if (checked && t == 0) { rH = pH; rC = pC; }   // step 0 only primes the pipeline: keep H(row0, 0)
 				T D = pH, DC = pC;
@@ -288,6 +308,26 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					const T kold = kbest;
 #pragma unroll
 					for (int r = 0; r < R; ++r) {
+						if (TAG) {
+							const T Mt = V::addmax(D, (T)pw[r], ZERO);          // HOME or diagonal code + 1 in bits 0-1
+							const T Lt = V::addmax(Lup, e8h4, MoUp);            // bit 2: extended
+							const T Ut = V::addmax(Ul[r], e8h, Mol[r]);         // bit 1: opened
+							const T Lk = Lt & ~V::raw(4);                       // clean | 2
+							const T Uk = Ut & ~V::raw(2);                       // clean
+							const T Mk = (Mt & ~V::raw(3)) | V::raw(1);         // clean | 1
+							Mo = Mk + o8p1;                                     // M + o, low bits 2
+							Hm = V::vmax3(Lk, Mk, Uk);                          // clean | code
+							// un-negated nibble into the accumulator (the word is inverted at the store); the shifted-in
+							// bits of the other half's oldest nibble are overwritten, so the word never needs a reset
+							const T s1 = (Mt & V::raw(3)) | (Lt & ~V::raw(3));
+							const T z = (s1 & V::raw(7)) | ((Ut * 4u) & ~V::raw(7));
+							acc[r] = ((acc[r] * 16u) & ~V::raw(15)) | (z & V::raw(15));
+							kbest = V::addmax(Mk, crow[r], kbest);
+							D = Hl[r];
+							Hl[r] = Hm; Ul[r] = Uk; Mol[r] = Mo;
+							Lup = Lk; MoUp = Mo; Ln = Lk;
+							continue;
+						}
 						T Mraw;                                                 // H(i-1,j-1) + s
 						if (PROF) Mraw = D + (T)pw[r];
 						else { const T tt = V::flag((T)(ac[r] ^ c), mu8); Mraw = tt * (T)nsg + D; }   // tt: 0 on a match, 8|m-u| otherwise
@@ -330,7 +370,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					if (MODE == MODE_LOCAL) note_best(kold, kbest, t);
 				} else {
 #pragma unroll
-					for (int r = 0; r < R; ++r) { acc[r] = first ? 0u : acc[r] * 16u; if (JUMP) accJ[r] *= 2u; }
+					for (int r = 0; r < R; ++r) { acc[r] = (first && !TAG) ? 0u : acc[r] * 16u; if (JUMP) accJ[r] *= 2u; }
 				}
 			};
 
@@ -355,7 +395,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 				if (want_ptr) {
 					uint32_t *w = ptr + ((size_t)(stripe * G + tb / SPW) * 32 + lane) * R;
 #pragma unroll
-					for (int r = 0; r < R; ++r) w[r] = acc[r];
+					for (int r = 0; r < R; ++r) w[r] = TAG ? ~acc[r] : acc[r];
 				}
 				if (JUMP && want_ptr && ((tb + SPW - 1u) & 31u) == 31u) {
 					uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (tb >> 5)) * 32 + lane) * R;
