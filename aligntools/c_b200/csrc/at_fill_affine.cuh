@@ -17,6 +17,8 @@
 //   * scores are kept x8; a and b being multiples of 8, a != b  =>  |a-b| >= 8, so a traceback
 //     flag is  min(max(a,b) - b, 1|3|4|8)  : one subtract (FMA-pipe IMAD.IADD) + one VIMNMX, and
 //     it lands on its bit of the pointer nibble without shifts;
+//     (packed lanes WITH the query profile -- the C2 path -- go further and carry every argmax in
+//     the spare low bits of the values themselves: see TAG below, one VIADDMNMX per flag);
 //   * packed lanes are BIASED by 0x8000 per half and compared unsigned, so every add/subtract is
 //     an ordinary 32-bit integer instruction (no carry can cross the halves while the values
 //     stay in range, which the host checks) and can be issued on the FMA pipe;
