@@ -61,7 +61,9 @@ class _Output(C.Structure):
 class _Timing(C.Structure):
     _fields_ = [("fill_ms", C.c_double), ("traceback_ms", C.c_double), ("device_ms", C.c_double),
                 ("cells", C.c_uint64), ("launches", C.c_uint64), ("ptr_bytes", C.c_uint64),
-                ("fill_kernel_ms", C.c_double), ("fill_kernel_cells", C.c_uint64)]
+                ("fill_kernel_ms", C.c_double), ("fill_kernel_cells", C.c_uint64),
+                ("fill_kernel_kind", C.c_uint32), ("fill_kernel_rows", C.c_uint32),
+                ("fill_kernel_flags", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 _lib = None
@@ -151,6 +153,9 @@ class Timing:
     ptr_bytes: int
     fill_kernel_ms: float
     fill_kernel_cells: int
+    fill_kernel_kind: int = 0       # enum at_kernel_kind
+    fill_kernel_rows: int = 0
+    fill_kernel_flags: int = 0
 
 
 def _mode(mode):
@@ -266,7 +271,7 @@ class Batch:
         if rc:
             raise AtError(rc, self.al.last_error())
         return Timing(tm.fill_ms, tm.traceback_ms, tm.device_ms, tm.cells, tm.launches, tm.ptr_bytes,
-                      tm.fill_kernel_ms, tm.fill_kernel_cells)
+                      tm.fill_kernel_ms, tm.fill_kernel_cells, tm.fill_kernel_kind, tm.fill_kernel_rows, tm.fill_kernel_flags)
 
     def fetch(self) -> BatchResult:
         res = BatchResult(self.n)
@@ -368,7 +373,7 @@ class Aligner:
         if rc:
             raise AtError(rc, self.last_error())
         res.timing = Timing(tm.fill_ms, tm.traceback_ms, tm.device_ms, tm.cells, tm.launches, tm.ptr_bytes,
-                            tm.fill_kernel_ms, tm.fill_kernel_cells)
+                            tm.fill_kernel_ms, tm.fill_kernel_cells, tm.fill_kernel_kind, tm.fill_kernel_rows, tm.fill_kernel_flags)
         return res
 
     def align(self, mode, reads, targets, opt: Opt = None, sites=None, out_flags=OUT_CIGAR | OUT_ALN) -> BatchResult:

@@ -39,7 +39,7 @@
 // ties;  U: open wins ties;  J: enter wins ties, entering forbidden on listed target indices.
 #pragma once
 
-namespace at {
+namespace atb2 {
 
 #define AT_RING 512        // target ring entries per warp (two 256-column blocks)
 #define AT_FILL_WARPS 4
@@ -451,4 +451,4 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 	}
 }
 
-}  // namespace at
+}  // namespace atb2

@@ -68,7 +68,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 	std::vector<UploadGate> gate(nd);          // uploads of a device's sub-slices go one at a time, in pair order
 	std::vector<std::atomic<size_t>> next(nd);
 	for (auto &x : next) x = 0;
-	struct Acc { double fill = 0, tb = 0, dev = 0, domk = 0; uint64_t domc = 0, launches = 0, ptr = 0; };
+	struct Acc { double fill = 0, tb = 0, dev = 0, domk = 0; uint64_t domc = 0, launches = 0, ptr = 0; uint32_t kind = 0, r = 0, flags = 0; };
 	std::vector<Acc> acc(nd * AT_PIPE_STREAMS);
 	const int n_workers = (int)std::min<uint64_t>(AT_PIPE_STREAMS, std::max<uint64_t>(1, env_u64("AT_PIPE_WORKERS", AT_PIPE_STREAMS)));   // diagnosis: fewer workers
 
@@ -134,7 +134,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 			if (trace) fprintf(stderr, "[at pipe] dev %zu stream %d slice %zu pairs %llu: setup %.2f-%.2f SMs %.2f-%.2f run -%.2f fetch -%.2f ms (fill %.2f tb %.2f)\n",
 			                   d, w, si, (unsigned long long)sub.n_pairs, t_a, t_b, t_lock, t_hand, t_c, now_ms(), s.fill_ms, s.tb_ms);
 			a.fill += s.fill_ms; a.tb += s.tb_ms; a.dev += s.dev_ms; a.launches += s.launches; a.ptr += traceback ? s.ptr_bytes : 0;
-			if (s.domk_cells > a.domc) { a.domc = s.domk_cells; a.domk = s.domk_ms; }
+			if (s.domk_cells > a.domc) { a.domc = s.domk_cells; a.domk = s.domk_ms; a.kind = s.domk_kind; a.r = s.domk_r; a.flags = s.domk_flags; }
 			if (rc) { std::lock_guard<std::mutex> lk(mu); failed = rc; cv.notify_all(); break; }
 		}
 	};
@@ -159,7 +159,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 			for (int w = 0; w < AT_PIPE_STREAMS; ++w) {
 				const Acc &a = acc[d * AT_PIPE_STREAMS + w];
 				fill += a.fill; tb += a.tb; dev += a.dev; timing->launches += a.launches; timing->ptr_bytes += a.ptr;
-				if (a.domc > timing->fill_kernel_cells) { timing->fill_kernel_cells = a.domc; timing->fill_kernel_ms = a.domk; }
+				if (a.domc > timing->fill_kernel_cells) { timing->fill_kernel_cells = a.domc; timing->fill_kernel_ms = a.domk; timing->fill_kernel_kind = a.kind; timing->fill_kernel_rows = a.r; timing->fill_kernel_flags = a.flags; }
 			}
 			timing->fill_ms = std::max(timing->fill_ms, fill); timing->traceback_ms = std::max(timing->traceback_ms, tb);
 			timing->device_ms = std::max(timing->device_ms, dev);     // sum of the sub-slices' device times (they overlap)
@@ -182,7 +182,8 @@ extern "C" int at_batch_align(at_handle *h, int mode, const at_params *p, const 
 		                                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
 		return align_pipelined(h, mode, p, in, out_flags, out, timing, prefix);
 	}
-	one_at_a_time.unlock();
+	// small batches: the plain three-call path, still under the handle's lock (include/aligntools_b200.h: a handle
+	// serves one batch operation at a time; concurrent callers of at_batch_align are serialised)
 	at_batch *b = nullptr;
 	int rc = at_batch_create(h, mode, p, in, out_flags, &b);
 	if (rc) return rc;

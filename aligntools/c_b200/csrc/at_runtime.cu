@@ -29,7 +29,7 @@
 #include <thread>
 #include <vector>
 
-using namespace at;
+using namespace atb2;
 
 // ------------------------------------------------------------------ handle ----
 struct at_device {
@@ -143,7 +143,13 @@ extern "C" void at_destroy(at_handle *h)
 	delete h;
 }
 
-extern "C" const char *at_last_error(const at_handle *h) { return h ? h->err.c_str() : ""; }
+extern "C" const char *at_last_error(const at_handle *h)
+{
+	if (!h) return "";
+	static thread_local std::string copy;      // another thread of the handle may be rewriting h->err
+	{ std::lock_guard<std::mutex> g(const_cast<at_handle *>(h)->mu); copy = h->err; }
+	return copy.c_str();
+}
 extern "C" int at_device_count(const at_handle *h) { return h ? (int)h->devs.size() : 0; }
 extern "C" uint64_t at_launch_count(const at_handle *h) { return h ? h->launches.load() : 0; }
 
@@ -211,7 +217,7 @@ struct Shard {
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t evk[2] = {nullptr, nullptr};
 	// last-run timing
-	double fill_ms = 0, tb_ms = 0, dev_ms = 0, domk_ms = 0; uint64_t domk_cells = 0, launches = 0;
+	double fill_ms = 0, tb_ms = 0, dev_ms = 0, domk_ms = 0; uint64_t domk_cells = 0, launches = 0; uint32_t domk_kind = 0, domk_r = 0, domk_flags = 0;
 	int rc = AT_OK;
 };
 
@@ -690,8 +696,15 @@ static int validate_batch(at_handle *h, int mode, const at_params *p, const at_b
 	if (in->encoding != AT_SEQ_BYTES && in->encoding != AT_SEQ_2BIT) return AT_E_ARG;
 	if ((in->sites == nullptr) != (in->site_off == nullptr)) return AT_E_ARG;
 	if (in->n_pairs >= (1ull << 31)) return AT_E_ARG;
+	if (in->site_off) {      // per-pair slices of `sites`: ascending offsets (build_jump_mask indexes with their differences)
+		for (uint64_t k = 0; k < in->n_pairs; ++k)
+			if (in->site_off[k + 1] < in->site_off[k] || in->site_off[k + 1] - in->site_off[0] > (1ull << 40)) { set_err(h, "site_off is not ascending at pair %llu", (unsigned long long)k); return AT_E_ARG; }
+	}
 	int64_t maxabs = std::max<int64_t>({llabs((long long)p->m), llabs((long long)p->u), llabs((long long)p->o), llabs((long long)p->e), llabs((long long)p->j), 1});
-	const uint64_t max_sum = (uint64_t)(((1ll << 27) - 1) / maxabs);      // (l1 + l2 + 2) * maxabs < 2^27
+	// Score lanes hold values x8.  With B = 8 (l1 + l2 + 2) maxabs bounding every finite value, a -inf stand-in
+	// (AT_NEG = -2^29, at_kernels.cuh) that has drifted by up to B must still lose against every finite value:
+	// AT_NEG + B < -B  <=>  (l1 + l2 + 2) * maxabs < 2^25.  (AT_NEG_INIT - B stays above INT32_MIN with room to spare.)
+	const uint64_t max_sum = (uint64_t)(((1ll << 25) - 1) / maxabs);
 	uint64_t *pre = nullptr;
 	if (prefix) { prefix->resize(in->n_pairs + 1); pre = prefix->data(); pre[0] = 0; }
 	// one pair's checks, in the reference's order of failure; `report` false = only say whether it fails
@@ -1036,7 +1049,11 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 		CU(h, cudaStreamSynchronize(st));
 		CU(h, cudaEventElapsedTime(&ms, e_begin, e_fill)); s.fill_ms += ms;
 		CU(h, cudaEventElapsedTime(&ms, e_fill, e_tb)); s.tb_ms += ms;
-		if ((int)ci == dom_chunk) { CU(h, cudaEventElapsedTime(&ms, s.evk[0], s.evk[1])); s.domk_ms = ms; s.domk_cells = dom_cells; }
+		if ((int)ci == dom_chunk) {
+			CU(h, cudaEventElapsedTime(&ms, s.evk[0], s.evk[1])); s.domk_ms = ms; s.domk_cells = dom_cells;
+			const Launch &dl = c.launches[dom_launch];
+			s.domk_kind = (uint32_t)dl.kind; s.domk_r = (uint32_t)dl.r; s.domk_flags = (s.prof ? 1u : 0u) | (jump ? 2u : 0u);
+		}
 		if (ci + 1 == s.chunks.size()) { CU(h, cudaEventElapsedTime(&ms, e_first, e_tb)); s.dev_ms = ms; }
 	}
 	h->launches += s.launches;
@@ -1059,7 +1076,7 @@ extern "C" int at_batch_run(at_batch *b, at_timing *timing)
 			timing->traceback_ms = std::max(timing->traceback_ms, s.tb_ms);
 			timing->device_ms = std::max(timing->device_ms, s.dev_ms);
 			timing->cells += s.cells; timing->launches += s.launches; timing->ptr_bytes += b->traceback ? s.ptr_bytes : 0;
-			if (s.domk_cells > timing->fill_kernel_cells) { timing->fill_kernel_cells = s.domk_cells; timing->fill_kernel_ms = s.domk_ms; }
+			if (s.domk_cells > timing->fill_kernel_cells) { timing->fill_kernel_cells = s.domk_cells; timing->fill_kernel_ms = s.domk_ms; timing->fill_kernel_kind = s.domk_kind; timing->fill_kernel_rows = s.domk_r; timing->fill_kernel_flags = s.domk_flags; }
 		}
 	}
 	return AT_OK;
@@ -1160,7 +1177,9 @@ extern "C" int64_t at_cigar_to_string(const uint32_t *ops, uint64_t n_ops, char 
 	uint64_t pos = 0;
 	for (uint64_t k = 0; k < n_ops; ++k) {
 		char buf[16];
-		const int len = snprintf(buf, sizeof buf, "%u%c", ops[k] >> 4, "MIDN"[ops[k] & 3]);
+		const uint32_t code = ops[k] & 15u;      // the format reserves four bits for the op code
+		if (code > AT_CIG_N) return -1;
+		const int len = snprintf(buf, sizeof buf, "%u%c", ops[k] >> 4, "MIDN"[code]);
 		if (pos + len + 1 > cap) return -1;
 		memcpy(dst + pos, buf, len); pos += len;
 	}

@@ -27,7 +27,7 @@
 #pragma once
 #include <type_traits>
 
-namespace at {
+namespace atb2 {
 
 #define AT_WAVE_WARPS 4
 constexpr int AT_WAVE_UNROLL_AFFINE = 2;     // steps per loop body (instruction-cache footprint, see the loops)
@@ -868,4 +868,4 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 	}
 }
 
-}  // namespace at
+}  // namespace atb2

@@ -10,6 +10,8 @@ gather of the per-rank result arrays (`gloo` on CPU hosts, `nccl`/`gloo` on GPU 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import BatchResult, plan_slices  # noqa: F401  (re-exported)
@@ -75,3 +77,71 @@ def gather_results(res, cut, rank, world, dst=0):
             setattr(p, k, v)
         parts.append(p)
     return merge_results(parts, cut)
+
+
+class HostGather:
+    """Results of a sharded batch gathered in rank 0's host memory WITHOUT a collective (ranks of one box): rank 0
+    owns shared-memory output arrays of the whole batch; every rank's at_batch_align writes its slice's scores /
+    cells straight into them at the slice offset and its CIGARs into its own shared region, which rank 0 then
+    concatenates in pair order (one memcpy per rank).  torch.distributed only carries the segment names (and the
+    caller's barrier); `tag` keeps the segment names of concurrent gathers apart."""
+
+    def __init__(self, dist, rank, world, n_pairs, cigar_cap_per_rank, tag):
+        from multiprocessing import shared_memory
+        self.rank, self.world, self.n = rank, world, n_pairs
+        self.cap = int(cigar_cap_per_rank)
+        self.sizes = {"score": 4 * n_pairs, "end_i": 4 * n_pairs, "end_j": 4 * n_pairs, "beg_i": 4 * n_pairs, "beg_j": 4 * n_pairs,
+                      "cigar_off": 8 * (n_pairs + world), "cigar": 4 * self.cap * world, "nops": 8 * world}
+        names = [None]
+        self.shm = {}
+        if rank == 0:
+            names = [{k: f"atb2_{tag}_{os.getpid()}_{k}" for k in self.sizes}]
+            for k, sz in self.sizes.items():
+                self.shm[k] = shared_memory.SharedMemory(name=names[0][k], create=True, size=max(sz, 8))
+        if world > 1:
+            dist.broadcast_object_list(names, src=0)
+        if rank != 0:
+            from multiprocessing import resource_tracker
+            for k in self.sizes:
+                self.shm[k] = shared_memory.SharedMemory(name=names[0][k])
+                try:      # the segments belong to rank 0: keep this process's tracker from unlinking them at exit
+                    resource_tracker.unregister(self.shm[k]._name, "shared_memory")
+                except Exception:
+                    pass
+        self.arr = {k: np.ndarray((self.sizes[k] // (8 if k in ("cigar_off", "nops") else 4),),
+                                  dtype=np.uint64 if k in ("cigar_off", "nops") else (np.int32 if k == "score" else np.uint32),
+                                  buffer=self.shm[k].buf) for k in self.sizes}
+
+    def slice_out(self, lo, hi):
+        """BatchResult whose arrays are views into the shared outputs at this rank's slice."""
+        r = BatchResult(0)
+        r.n = hi - lo
+        for k in ("score", "end_i", "end_j", "beg_i", "beg_j"):
+            setattr(r, k, self.arr[k][lo:hi])
+        base = lo + self.rank                      # every rank's offsets take n_slice + 1 entries
+        r.cigar_off = self.arr["cigar_off"][base:base + (hi - lo) + 1]
+        r.cigar = self.arr["cigar"][self.rank * self.cap:(self.rank + 1) * self.cap]
+        return r
+
+    def merge(self, cut, dst_cigar, dst_off):
+        """rank 0: dense CIGARs of the whole batch in pair order."""
+        base = 0
+        for r in range(self.world):
+            lo, hi = int(cut[r]), int(cut[r + 1])
+            offs = self.arr["cigar_off"][lo + r:lo + r + (hi - lo) + 1]
+            k = int(offs[-1]) if hi > lo else 0
+            dst_off[lo:hi] = offs[:-1] + np.uint64(base)
+            dst_cigar[base:base + k] = self.arr["cigar"][r * self.cap:r * self.cap + k]
+            base += k
+        dst_off[self.n] = base
+        return base
+
+    def close(self):
+        self.arr = None
+        for s in self.shm.values():
+            try:
+                s.close()
+                if self.rank == 0:
+                    s.unlink()
+            except Exception:
+                pass

@@ -29,6 +29,20 @@ def _ragged_batch(seqs):
     return np.ascontiguousarray(np.concatenate(seqs)), off, lens
 
 
+# the two protein records of the reference's test/test_global.fa (BASELINE.json configs[0]); the same strings
+# are kept with their md5 in tests/golden/cli_vectors.json
+C1_S1 = b"PAKKFQIFWEKQHMIYHFTFIYVDTLICILFIVAKAGTLRFEHPHSWCRHVVDYSIGNYWSVWTVNEAYRSG"
+C1_S2 = b"PAKKLCHDCTDPIVWEKQHMIYHFTFIYVDTLICILFIVAKAGTLRDEHPVSWCRHVVEDYSIGNYWSVWTVNEAYRSG"
+
+
+def config1_global(n_pairs=1):
+    """C1: global alignment of test/test_global.fa with -m 1 -u -1 -o -4 -e -1 (72 x 79, protein bytes)."""
+    q, qo, ql = _ragged_batch([np.frombuffer(C1_S1, np.uint8)] * n_pairs)
+    t, to, tl = _ragged_batch([np.frombuffer(C1_S2, np.uint8)] * n_pairs)
+    return dict(mode="global", params=dict(m=1, u=-1, o=-4, e=-1, j=-10, jump=False),
+                q=q, q_off=qo, q_len=ql, t=t, t_off=to, t_len=tl, sites=None, site_off=None)
+
+
 def config2_local(n_pairs=1 << 20, l1=150, l2=500, stream=0):
     """C2: local, reads of l1 bp against l2 bp target windows: read = window of the target with
     4 % substitutions, 1 % insertions, 1 % deletions; 10 % of the pairs are unrelated."""

@@ -160,7 +160,19 @@ typedef struct at_timing {
 	uint64_t ptr_bytes;      /* traceback-pointer bytes written to HBM                               */
 	double   fill_kernel_ms; /* average duration of ONE launch of the dominant fill kernel           */
 	uint64_t fill_kernel_cells; /* cells one such launch processes                                   */
+	uint32_t fill_kernel_kind;  /* which kernel that was: enum at_kernel_kind                            */
+	uint32_t fill_kernel_rows;  /* its rows per lane (AT_K_EDIT_BITS: 32-row blocks per lane)            */
+	uint32_t fill_kernel_flags; /* bit 0: query-profile variant, bit 1: jump state, bit 2: 2-bit targets */
+	uint32_t reserved_;
 } at_timing;
+
+/* kernels a fill launch can be (at_timing.fill_kernel_kind) */
+enum at_kernel_kind {
+	AT_K_FILL_INT32  = 0,  /* at_fill_affine, int32 lanes, one pair per warp            */
+	AT_K_FILL_S16X2  = 1,  /* at_fill_affine, packed s16x2 lanes, two pairs per warp    */
+	AT_K_WAVE        = 2,  /* at_wave_affine / at_wave_linear, stripes of one pair      */
+	AT_K_EDIT_BITS   = 3   /* at_wave_edit_bits, bit-parallel unit-cost edit distance   */
+};
 
 typedef struct at_batch at_batch;
 

@@ -140,3 +140,39 @@ def test_port_medium_vs_reference(oracle_mod):
     b = oracle_mod.ref_align("overlap", s1, s2, p)
     assert (a.score, a.r1, a.r2) == (b.score, b.r1, b.r2)
     assert a.score > 1000
+
+
+@pytest.mark.parametrize("mode", ["global", "local", "fitjump", "overlap", "edit"])
+def test_port_20kbp_vs_reference(oracle_mod, mode):
+    """the port is the checker of the long-sequence GPU tests, so it is itself pinned against the
+    compiled reference at the largest size the reference's 48 B/cell matrices allow here: one 20 kbp x 20 kbp pair
+    per mode (fit: 16 kbp x 20 kbp, with junction sites)."""
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(2026 + len(mode))
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    l2 = 20000
+    s2 = acgt[rng.integers(0, 4, l2)]
+    if mode == "fitjump":                      # transcript of two "exons" of the target, 3 % substitutions
+        s1 = np.concatenate([s2[1000:9000], s2[11000:19000]]).copy()
+        sites = [8999, 9000, 10999, 11000, 15000]
+    else:
+        s1 = s2.copy()
+        cut = np.sort(rng.choice(l2, 400, replace=False))
+        s1 = np.delete(s1, cut[:200])                                  # 1 % deletions, 1 % insertions
+        s1 = np.insert(s1, np.sort(rng.choice(s1.size, 200)), acgt[rng.integers(0, 4, 200)])
+        sites = None
+    sub = rng.random(s1.size) < 0.03
+    s1[sub] = acgt[rng.integers(0, 4, int(sub.sum()))]
+    if mode == "overlap":                      # s2's prefix overlaps s1's suffix
+        s1 = np.concatenate([acgt[rng.integers(0, 4, 6000)], s1[:14000]])
+    p = oracle_mod.Params(1, -2, -5, -1, -10, mode == "fitjump") if mode != "edit" else oracle_mod.Params(1, 1, -5, -1, -10, False)
+    md = "fit" if mode == "fitjump" else mode
+    a = oracle_mod.port_align(md, s1.tobytes(), s2.tobytes(), p, sites)
+    b = oracle_mod.ref_align(md, s1.tobytes(), s2.tobytes(), p, sites)
+    assert a.score == b.score
+    if md != "edit":
+        assert (a.r1, a.r2) == (b.r1, b.r2)
+        assert len(a.r1) > 10000
+    if mode == "fitjump":
+        assert a.ops.count(b"N") > 1000

@@ -91,3 +91,73 @@ def test_two_rank_gloo_sharded_gather(tmp_path, oracle_mod):
     port = 29000 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def _worker_shm(rank, world, port, tmpdir):
+    """HostGather: every rank writes its slice straight into rank 0's shared-memory output arrays."""
+    import torch.distributed as dist
+    import aligntools.c_b200 as A
+    from aligntools.c_b200 import sharding
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q, t = _batch(70, seed=21)
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    n = len(ql)
+    cut = sharding.plan_slices(ql, tl, world)
+    lo, hi = sharding.rank_slice(cut, rank)
+    p = oracle.Params(2, -3, -4, -1, -10, False)
+    cap = 4096
+    hg = sharding.HostGather(dist, rank, world, n, cap, "t")
+    out = hg.slice_out(lo, hi)
+
+    def rle_ops(ops):         # per-column op letters -> packed run-length ops (AT_CIG_*)
+        res, k = [], 0
+        while k < len(ops):
+            j = k
+            while j < len(ops) and ops[j] == ops[k]:
+                j += 1
+            res.append(((j - k) << 4) | b"MIDN".index(ops[k]))
+            k = j
+        return res
+
+    # stands in for at_batch_align on this rank's GPU: fills the caller-provided (shared) output views
+    ref = oracle.port_batch("local", p, qb, qo[lo:hi + 1].copy(), ql[lo:hi].copy(), tb, to[lo:hi + 1].copy(), tl[lo:hi].copy(),
+                            want_aln=True, want_ops=True, threads=1)
+    out.score[:] = ref.score
+    out.end_i[:], out.end_j[:] = ref.coords[:, 0], ref.coords[:, 1]
+    out.beg_i[:], out.beg_j[:] = ref.coords[:, 2], ref.coords[:, 3]
+    pos = 0
+    for k in range(hi - lo):
+        out.cigar_off[k] = pos
+        for op in rle_ops(ref.op(k)):
+            out.cigar[pos] = op; pos += 1
+    out.cigar_off[hi - lo] = pos
+    dist.barrier()
+    if rank == 0:
+        full_c = np.zeros(cap * world, np.uint32); full_off = np.zeros(n + 1, np.uint64)
+        tot = hg.merge(cut, full_c, full_off)
+        whole = oracle.port_batch("local", p, qb, qo, ql, tb, to, tl, want_aln=True, want_ops=True, threads=1)
+        assert np.array_equal(hg.arr["score"][:n].astype(np.int64), whole.score)
+        assert np.array_equal(hg.arr["end_j"][:n], whole.coords[:, 1].astype(np.uint32))
+        pos = 0
+        for k in range(n):
+            ops = rle_ops(whole.op(k))
+            assert int(full_off[k]) == pos and list(full_c[pos:pos + len(ops)]) == ops, k
+            pos += len(ops)
+        assert tot == pos == int(full_off[n])
+        open(os.path.join(tmpdir, "ok_shm"), "w").write("1")
+    dist.barrier()
+    hg.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shared_memory_host_gather(tmp_path, oracle_mod):
+    import torch.multiprocessing as mp
+    import aligntools.c_b200 as A
+    A.build()
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_worker_shm, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok_shm").exists()
