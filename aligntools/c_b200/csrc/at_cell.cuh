@@ -1,0 +1,223 @@
+// at_cell.cuh -- the Gotoh cell update shared by K1 (at_fill_affine.cuh) and K2's affine kernel
+// (at_wavefront.cuh): one cell of M / L / U (/ J) with the argmax of every max carried in the low bits of
+// the values and the traceback pointers assembled on the FMA pipe.  Host + device: the same source is compiled
+// by g++ into tests/cell_model (tests/test_cell_model.py checks it against the oracle without a GPU).
+//
+// Why it looks like this (ncu / SASS of round 1's kernels: the ALU pipe -- VIMNMX, VIADDMNMX, LOP3, IADD3 -- was
+// 90 % busy while the FMA pipe -- IMAD -- idled; both issue one warp instruction per two cycles per SM
+// sub-partition, so work moved from the ALU to the FMA pipe is free until the two are level):
+//
+//   * scores are kept x8: the three spare low bits of every value carry a TAG.  A candidate enters its max with
+//     a tie-break tag, so ONE VIADDMNMX gives the value AND its argmax (first-strictly-greater rules of max5,
+//     src/alignment.h:90-100, reproduced by the order of the tags):
+//         H tags = 3 - pointer code:  L 3, M 2, U 1, JUMP / HOME 0   (L wins ties, then M, then U: SURVEY A.0)
+//         Mo' = M + o carries tag 3;  L: extend (tag 3 + 4 = 7) beats open (3) on ties (:456);
+//         U: open (3) beats extend (1) on ties (:460);  J: enter (3 - 2 = 1) beats stay (0) on ties (:660);
+//         local M: the diagonal (tag >= 1) beats HOME = 0.0 (tag 0) on ties (:825).
+//   * one LOP3 per propagated value drops the tag again (Lk = Lt & ~4, Uk = Ut & ~2, Mk = (Mt & ~3) | 2,
+//     Jk = Jt & ~1); these CLEAN values are what the next cells consume;
+//   * the pointer nibble of a cell is a LINEAR function of (tagged - clean):
+//         nibble = 13 + (Mk + Lk + 4 Uk) - (Mt + Lt + 4 Ut)
+//       = (3 - tag of M) + 4 [L opened] + 8 [U extended]      (K3's layout, at_kernels.cuh header)
+//     so the kernels keep one accumulator per row, X = 16 X + (Mk + Lk + 4 Uk) - (Mt + Lt + 4 Ut) -- six
+//     adds / multiply-adds on the FMA pipe, no shifts / masks / selects on the ALU pipe -- and store
+//     X + 0xDDDDDDDD once per pointer word.  All of it is arithmetic mod 2^32, also for packed s16x2 lanes:
+//     the per-half nibble sums never exceed 16 bits, so carries between the halves cancel in the sum.
+//     The jump-bit plane works the same way: XJ = 2 XJ + (Jt - Jk), word = ~XJ.
+//
+// Reference recurrences: src/alignment.h:451-462 (global), :635-667 (fit + jump), :825-841 (local).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AT_HD __host__ __device__ __forceinline__
+#else
+#define AT_HD inline
+#endif
+
+namespace atb2 {
+
+enum { TAG_J = 0, TAG_U = 1, TAG_M = 2, TAG_L = 3 };      // tag of the winner of H = max(L, M, U[, J]); pointer code = 3 - tag
+#define AT_PTR_BIAS 0xDDDDDDDDu                            // 13 per nibble (see above)
+
+// -INFINITY stand-in in the x8-scaled score domain of the int32 lanes: a NEG-like value (AT_NEG
+// plus up to B = 8 (l1+l2+2) max|param| of drift) never beats a finite one (>= -B) as long as 2 B < 2^29, i.e.
+// (l1+l2+2)*max|param| < 2^25, which the host checks (validate_batch -> AT_E_RANGE).
+#define AT_NEG (-(1 << 29))
+#define AT_NEG_INIT (-(1 << 30) - (1 << 29))
+
+template <bool PACKED> struct Lanes;
+
+// int32 lanes: one pair per warp
+template <> struct Lanes<false> {
+	typedef int32_t T;
+	static constexpr uint32_t STEPS_PER_WORD = 8;
+	static AT_HD T rep(int v) { return v; }                                  // small constant in every lane half
+	static AT_HD T value(int v) { return 8 * v; }                            // a score
+	static AT_HD T delta(int v) { return 8 * v; }                            // score difference, for plain adds
+	static AT_HD T delta_h(int v) { return 8 * v; }                          // score difference, for the fused add of addmax
+	static AT_HD T addmax(T a, T b, T c)
+	{
+#ifdef __CUDA_ARCH__
+		return __viaddmax_s32(a, b, c);
+#else
+		const T s = (T)((uint32_t)a + (uint32_t)b); return s > c ? s : c;
+#endif
+	}
+	static AT_HD T vmax(T a, T b) { return a > b ? a : b; }
+	static AT_HD T vmax3(T a, T b, T c)
+	{
+#ifdef __CUDA_ARCH__
+		return __vimax3_s32(a, b, c);
+#else
+		return vmax(vmax(a, b), c);
+#endif
+	}
+};
+
+// packed s16x2 lanes: TWO pairs per warp, pair A in bits 0-15 and pair B in bits 16-31 of every register.
+// Values are BIASED by 0x8000 per half and compared unsigned (VIADDMNMX.U16x2 / VIMNMX3.U16x2), so every plain
+// add / subtract is an ordinary 32-bit integer instruction: no carry crosses the halves while the values stay in
+// range, which the host checks.
+template <> struct Lanes<true> {
+	typedef uint32_t T;
+	static constexpr uint32_t STEPS_PER_WORD = 4;
+	static AT_HD T rep(int v) { return (uint32_t)v * 0x10001u; }
+	static AT_HD T value(int v) { return (uint32_t)(8 * v * 0x10001) + 0x80008000u; }
+	static AT_HD T delta(int v) { return (uint32_t)(8 * v * 0x10001); }                     // exact 32-bit sum of both halves
+	static AT_HD T delta_h(int v) { return ((uint32_t)(8 * v) & 0xffffu) * 0x10001u; }      // two's complement per half
+	static AT_HD T addmax(T a, T b, T c)
+	{
+#ifdef __CUDA_ARCH__
+		return __viaddmax_u16x2(a, b, c);
+#else
+		const uint32_t lo = (a + b) & 0xffffu, hi = ((a >> 16) + (b >> 16)) & 0xffffu;
+		const uint32_t clo = c & 0xffffu, chi = c >> 16;
+		return (lo > clo ? lo : clo) | ((hi > chi ? hi : chi) << 16);
+#endif
+	}
+	static AT_HD T vmax(T a, T b)
+	{
+#ifdef __CUDA_ARCH__
+		return __vmaxu2(a, b);
+#else
+		const uint32_t lo = (a & 0xffffu) > (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu);
+		const uint32_t hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
+		return lo | (hi << 16);
+#endif
+	}
+	static AT_HD T vmax3(T a, T b, T c)
+	{
+#ifdef __CUDA_ARCH__
+		return __vimax3_u16x2(a, b, c);
+#else
+		return vmax(vmax(a, b), c);
+#endif
+	}
+};
+
+// Hide a value's provenance from the compiler (no instruction is emitted).  Without it LLVM rewrites
+// (ut & ~2) * 4 as (ut * 4) & ~8 to share the shift with ut * 4 -- one IMAD less, one LOP3 more, on the pipe that
+// binds these kernels.
+template <typename T> AT_HD T opaque(T v)
+{
+#ifdef __CUDA_ARCH__
+	asm("" : "+r"(v));
+#endif
+	return v;
+}
+
+// values of the k_and / k_or kernel arguments (see CellConst::set)
+template <bool PACKED> AT_HD uint32_t cell_k_and() { return (uint32_t)~Lanes<PACKED>::rep(3); }
+template <bool PACKED> AT_HD uint32_t cell_k_or() { return (uint32_t)Lanes<PACKED>::rep(TAG_M); }
+
+// Constants of one kernel instance (they live in registers / uniform registers).
+template <bool PACKED> struct CellConst {
+	typedef typename Lanes<PACKED>::T T;
+	T zero;        // local: the HOME candidate 0.0 (tag 0)
+	T e_l;         // 8 e + 4, fused-add form: L extends with tag 3 + 4 = 7
+	T e_u;         // 8 e, fused-add form: U extends with tag 1
+	T o_m;         // 8 o + 1, plain-add form: Mo' = Mk + o_m carries tag 3
+	T m_and, m_or; // Mk = (Mt & m_and) | m_or = clean | 2, as registers
+	T j_enter;     // 8 (jump - o) - 2, fused-add form: entering J from Mo' carries tag 1
+	T j_barred;    // the same on a black-listed target index: -inf
+	// k_and / k_or: ~3 and TAG_M in every lane half, handed in as KERNEL ARGUMENTS: constants the compiler can see
+	// become immediates, and a LOP3 takes only one -- (x & c1) | c2 would be two instructions on the binding pipe;
+	// with both in registers it is one
+	AT_HD void set(int o, int e, int jp, uint32_t k_and, uint32_t k_or)
+	{
+		typedef Lanes<PACKED> V;
+		zero = V::value(0);
+		e_l = V::delta_h(e) + V::rep(4);
+		e_u = V::delta_h(e);
+		o_m = V::delta(o) + V::rep(1);
+		m_and = (T)k_and;
+		m_or = (T)k_or;
+		j_enter = PACKED ? (T)0 : (T)(8 * (jp - o) - 2);
+		j_barred = PACKED ? (T)0 : (T)AT_NEG;
+	}
+};
+
+// State of one row between two columns (registers of the lane that owns the row).
+template <bool PACKED, bool JUMP> struct RowState {
+	typedef typename Lanes<PACKED>::T T;
+	T mo;          // M(i, j-1) + o, tag 3
+	T u;           // U(i, j-1), tag 1
+	T h;           // H(i, j-1) = max(L, M, U[, J]), tag of the winner
+	T j;           // J(i, j-1), tag 0 (JUMP only)
+	uint32_t x;    // pointer-word accumulator: 16 x + (clean - tagged) per step
+	uint32_t xj;   // jump-bit plane accumulator: 2 xj + (tagged - clean) per step (JUMP only)
+};
+
+// What a cell hands to the row below it (same column) and to the kernel's end-cell logic.
+template <bool PACKED> struct CellOut {
+	typedef typename Lanes<PACKED>::T T;
+	T lk;          // L(i, j) clean, tag 3     -> Lup of row i+1
+	T mo;          // M(i, j) + o, tag 3       -> MoUp of row i+1
+	T mk;          // M(i, j) clean, tag 2     (local: running maximum; fit: last-row search)
+	T h;           // H(i, j), tagged          (global: the corner)
+};
+
+// One cell.  d: H(i-1, j-1) tagged; pw: 8 s(i, j) (LOCAL && FUSED: fused-add form, else plain-add form);
+// lup / mo_up: L(i-1, j) clean and M(i-1, j) + o; jadd: c.j_enter or c.j_barred for this column; mul: 16, or 0 on the
+// first step of a pointer word (packed lanes restart their accumulators: the halves must not spill into each
+// other); mulj: 2, or 0 on the first step of a jump-plane word.  Returns the new D for the row below: H(i, j-1).
+template <int MODE_LOCAL_, bool JUMP, bool PACKED, bool FUSED>
+AT_HD typename Lanes<PACKED>::T cell_update(const CellConst<PACKED> &c, RowState<PACKED, JUMP> &st, const typename Lanes<PACKED>::T d,
+                                            const typename Lanes<PACKED>::T pw, const typename Lanes<PACKED>::T lup,
+                                            const typename Lanes<PACKED>::T mo_up, const typename Lanes<PACKED>::T jadd,
+                                            const uint32_t mul, const uint32_t mulj, CellOut<PACKED> &out)
+{
+	typedef Lanes<PACKED> V;
+	typedef typename V::T T;
+	T mt;
+	if (MODE_LOCAL_) mt = FUSED ? V::addmax(d, pw, c.zero) : V::vmax((T)(d + pw), c.zero);      // HOME: 0.0 strictly greater (:825)
+	else mt = d + pw;                                                                           // the diagonal's tag rides along
+	const T lt = V::addmax(lup, c.e_l, mo_up);           // tag 7: extended (ties included, :456), 3: opened
+	const T ut = V::addmax(st.u, c.e_u, st.mo);          // tag 1: extended, 3: opened (ties included, :460)
+	const T mk = opaque<T>((mt & c.m_and) | c.m_or);
+	const T lk = opaque<T>(lt & ~V::rep(4));
+	const T uk = opaque<T>(ut & ~V::rep(2));
+	const T mo = mk + c.o_m;
+	T h = V::vmax3(lk, mk, uk);
+	T jk = 0, jt = 0;
+	if (JUMP) {
+		jt = V::addmax(st.mo, jadd, st.j);               // tag 1: entered from M(i, j-1) (ties included, :660), 0: stayed
+		jk = opaque<T>(jt & ~V::rep(1));
+		h = V::vmax(h, jk);                              // J is the last argument of max5: it wins only when strictly greater
+	}
+	// pointer accumulator (FMA pipe): clean minus tagged, earliest step in the top nibble
+	st.x = st.x * mul + (((uint32_t)(lk + mk) - (uint32_t)(lt + mt)) + (uint32_t)uk * 4u - (uint32_t)ut * 4u);
+	if (JUMP) st.xj = st.xj * mulj + ((uint32_t)jt - (uint32_t)jk);
+	const T d_next = st.h;
+	st.h = h; st.u = uk; st.mo = mo;
+	if (JUMP) st.j = jk;
+	out.lk = lk; out.mo = mo; out.mk = mk; out.h = h;
+	return d_next;
+}
+
+// the word a row stores after STEPS_PER_WORD steps / after 32 steps of the jump plane
+AT_HD uint32_t ptr_word(uint32_t x) { return x + AT_PTR_BIAS; }
+AT_HD uint32_t jump_word(uint32_t xj) { return ~xj; }
+
+}  // namespace atb2

@@ -36,18 +36,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "at_cell.cuh"      // Lanes<>, cell_update(), AT_NEG: the cell arithmetic shared by K1 and K2
 
 namespace atb2 {
 
 enum { MODE_GLOBAL = 0, MODE_LOCAL = 1, MODE_FIT = 2, MODE_OVERLAP = 3, MODE_EDIT = 4 };
 enum { ST_LOW = 0, ST_MID = 1, ST_UPP = 2, ST_JUMP = 3 };   // also the 2-bit pointerM codes
 enum { CIG_M = 0, CIG_I = 1, CIG_D = 2, CIG_N = 3 };
-
-// -INFINITY stand-in in the x8-scaled score domain: a NEG-like value (AT_NEG plus up to
-// B = 8 (l1+l2+2) max|param| of drift) never beats a finite one (>= -B) as long as 2 B < 2^29, i.e.
-// (l1+l2+2)*max|param| < 2^25, which the host checks (validate_batch -> AT_E_RANGE).
-#define AT_NEG (-(1 << 29))
-#define AT_NEG_INIT (-(1 << 30) - (1 << 29))
 
 __device__ __forceinline__ uint32_t steps_last(uint32_t l2, int align_mask) { return (l2 + 31u) | (uint32_t)align_mask; }
 

@@ -942,6 +942,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				wa.score = s.d_score.p; wa.end_i = s.d_end_i.p; wa.end_j = s.d_end_j.p; wa.end_state = s.d_end_state.p;
 				wa.m = b->prm.m; wa.u = b->prm.u; wa.o = b->prm.o; wa.e = b->prm.e; wa.jp = b->prm.j;
 				wa.want_ptr = b->traceback ? 1 : 0;
+				wa.k_and = cell_k_and<false>(); wa.k_or = cell_k_or<false>();
 				void *kargs[] = {(void *)&wa};
 				CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warps), kargs, 0, st));
 			} else {
@@ -954,6 +955,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
 				fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
 				fa.want_ptr = b->traceback ? 1 : 0;
+				fa.k_and = l.kind == LK_PACKED ? cell_k_and<true>() : cell_k_and<false>(); fa.k_or = l.kind == LK_PACKED ? cell_k_or<true>() : cell_k_or<false>();
 				void *kargs[] = {(void *)&fa};
 				CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warps), kargs, dyn_smem, st));
 			}

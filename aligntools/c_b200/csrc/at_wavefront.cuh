@@ -55,6 +55,7 @@ struct WaveArgs {
 	const uint8_t  *symmap;  // at_wave_edit_bits: byte -> code 0..7 of the shard's READ alphabet, 8 = not in it;
 	                         // at_wave_linear<.., PROF>: byte -> code 0..3 of the shard's TARGET alphabet
 	uint32_t        syms;    // PROF: the byte of code c in bits 8c..8c+7
+	uint32_t        k_and, k_or;   // affine kernel: cell_k_and / cell_k_or (at_cell.cuh: constants that must stay in registers)
 };
 
 // ---- TMA (bulk async copy) + mbarrier + release/acquire helpers ----
@@ -151,12 +152,18 @@ __device__ __forceinline__ void wait_columns(const uint32_t *prog, uint32_t need
 // =====================================================================================
 // Affine kernel: global / local / fit (+jump), int32 lanes, R = 8 rows per lane.
 // =====================================================================================
+// The cell is cell_update() of at_cell.cuh (tagged values, pointer nibbles assembled on the FMA pipe), as in K1.
 // PROF (targets of the shard use at most four distinct bytes): query profile in shared memory as in K1,
-// prof[code][lane][r] = 8 * s(read row, target symbol); the carried H then holds H, not H + m.
+// prof[code][lane][r] = 8 * s(read row, target symbol); otherwise the xor / min form.
+// Lane 0's upper neighbour is matrix row 0 (first stripe) or the boundary row of the stripe above (a predicated
+// LDS from the boundary ring); it enters through a multiply-add with a 0/1 lane mask, not a branch.
+// Boundary element (int4 per column): x = M + o (tag 3), y = L (tag 3), z = H (tagged), w unused.
 template <int MODE, bool JUMP, bool PROF>
-__global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveArgs a)
+__global__ void __launch_bounds__(32 * AT_WAVE_WARPS, 4) at_wave_affine(const WaveArgs a)
 {
+	typedef Lanes<false> V;
 	constexpr int R = 8, RPP = 32 * R;
+	constexpr bool LOCAL = MODE == MODE_LOCAL;
 	constexpr int LS = prof_lane_stride(R);
 	struct __align__(16) Smem { int prof[PROF ? 4 : 1][PROF ? 32 : 1][PROF ? LS : 2]; WaveRing<JUMP> rg; int4 cring[64]; int4 stage[64]; };
 	__shared__ Smem sm_all[AT_WAVE_WARPS];
@@ -169,11 +176,15 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 	uint32_t ring_par = 0;      // bit s: parity of the next completion of slot s's mbarrier
 
 	const int m = a.m, u = a.u, o = a.o, e = a.e;
-	const int m8 = PROF ? 0 : 8 * m, o8 = 8 * o, e8 = 8 * e;      // m8: what the carried H holds on top of H (H + m in the xor/min variant)
+	CellConst<false> cc;
+	cc.set(o, e, a.jp, a.k_and, a.k_or);
+	const int m8 = 8 * m, o8 = 8 * o, e8 = 8 * e;
 	const uint32_t mu8 = (uint32_t)(8 * (m >= u ? m - u : u - m));
 	const int nsg = m >= u ? -1 : 1;
 	const int ZERO = 0, NEGV = AT_NEG;
 	const bool want_ptr = a.want_ptr != 0;
+	int nz = lane ? 1 : 0;                                                     // lane 0 takes the row above the stripe instead of a neighbour
+	asm volatile("" : "+r"(nz));                                               // opaque: keep x * nz + b a multiply-add (FMA pipe), not a SEL
 
 	for (;;) {
 		uint32_t job = 0;
@@ -203,13 +214,16 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 		const uint32_t *prog_in = a.prog + (stripe ? job - 1 : job);
 		uint32_t seen = 0;
 		const uint32_t row0 = stripe * RPP + lane * R;
+		const bool feed = lane == 0 && stripe > 0;                         // this lane reads the boundary ring
+		const bool park = lane == 31 && !last_stripe;                      // this lane parks its last row for the next stripe
 
 		__syncwarp();
 		if (n_tiles > 0) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 0, lane);
 		if (n_tiles > 1) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 1, lane);
 
-		int Mol[R], Ul[R], Hl[R], Cl[R], Jl[R], crow[R];
-		uint32_t ac[R], acc[R], accJ[R];
+		RowState<false, JUMP> st[R];
+		int crow[R];
+		uint32_t ac[R];
 #pragma unroll
 		for (int r = 0; r < R; ++r) {
 			const uint32_t ri = row0 + r;
@@ -220,29 +234,42 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 #pragma unroll
 				for (int c = 0; c < 4; ++c) sm.prof[c][lane][r] = 8 * (qa == ((a.syms >> (8 * c)) & 255u) ? m : u);
 			}
-			crow[r] = ri < l1 ? 7 - r : -(1 << 28);
-			if (MODE == MODE_GLOBAL)     { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = 8 * (o + e * i) + m8; Cl[r] = ST_LOW; }      // :432-436
-			else if (MODE == MODE_LOCAL) { Mol[r] = ZERO + o8; Ul[r] = ZERO; Hl[r] = ZERO + m8; Cl[r] = ST_LOW; }           // calloc zeros
-			else                         { Mol[r] = NEGV; Ul[r] = NEGV; Hl[r] = NEGV; Cl[r] = ST_MID; }                     // :612-617
-			Jl[r] = NEGV; acc[r] = 0; accJ[r] = 0;
+			crow[r] = ri < l1 ? 5 - r : -(1 << 28);                       // on top of Mk = 8 M + 2: key = 8 M + 7 - r
+			// column 0 (left border), tags as cell_update leaves them
+			if (MODE == MODE_GLOBAL)     { st[r].mo = NEGV | 3; st[r].u = NEGV | 1; st[r].h = 8 * (o + e * i) | TAG_L; }      // :432-436
+			else if (MODE == MODE_LOCAL) { st[r].mo = ZERO + o8 + 3; st[r].u = ZERO | 1; st[r].h = ZERO | TAG_L; }            // calloc zeros
+			else                         { st[r].mo = NEGV | 3; st[r].u = NEGV | 1; st[r].h = NEGV | TAG_M; }                 // :612-617
+			st[r].j = NEGV; st[r].x = 0; st[r].xj = 0;
 		}
 		if (PROF) __syncwarp();
-		int sM = Mol[R - 1], sH = Hl[R - 1], sC = Cl[R - 1];
-		int sL = MODE == MODE_GLOBAL ? 8 * (o + e * (int)(row0 + R)) : (MODE == MODE_LOCAL ? ZERO : NEGV);
-		int pH, pC;      // H(row0, 0) + m and its code: the row above this lane's strip, column 0
+		int sM = st[R - 1].mo, sH = st[R - 1].h;
+		int sL = MODE == MODE_GLOBAL ? (8 * (o + e * (int)(row0 + R)) | 3) : (MODE == MODE_LOCAL ? (ZERO | 3) : (NEGV | 3));
+		int pH;      // H(row0, 0): the row above this lane's strip, column 0
 		if (row0 == 0) {
-			if (MODE == MODE_GLOBAL)     { pH = 8 * (o < 0 ? 0 : o) + m8; pC = o < 0 ? ST_MID : ST_LOW; }                    // max5(L=o, M=0, U=o)
-			else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = ST_LOW; }
-			else                         { pH = ZERO + m8; pC = ST_MID; }                                                    // M[0][0]=U[0][0]=0
+			if (MODE == MODE_GLOBAL)     pH = 8 * (o < 0 ? 0 : o) | (o < 0 ? TAG_M : TAG_L);                                 // max5(L=o, M=0, U=o)
+			else if (MODE == MODE_LOCAL) pH = ZERO | TAG_L;
+			else                         pH = ZERO | TAG_M;                                                                  // M[0][0]=U[0][0]=0
 		} else {
-			if (MODE == MODE_GLOBAL)     { pH = 8 * (o + e * (int)row0) + m8; pC = ST_LOW; }
-			else if (MODE == MODE_LOCAL) { pH = ZERO + m8; pC = ST_LOW; }
-			else                         { pH = NEGV; pC = ST_MID; }
+			if (MODE == MODE_GLOBAL)     pH = 8 * (o + e * (int)row0) | TAG_L;
+			else if (MODE == MODE_LOCAL) pH = ZERO | TAG_L;
+			else                         pH = NEGV | TAG_M;
+		}
+		// what lane 0 adds instead of a neighbour's row (zero in every other lane): matrix row 0 in the first stripe,
+		// the boundary ring's element of the column otherwise (loaded per step by lane 0 alone)
+		int4 bq = make_int4(0, 0, 0, 0);
+		int b0E = 0;
+		if (lane == 0 && stripe == 0) {
+			if (MODE == MODE_GLOBAL)     { bq.x = NEGV | 3; bq.y = NEGV | 3; bq.z = 8 * o | TAG_U; b0E = e8; }                // :437-441, U[0][j] = o + e j
+			else if (MODE == MODE_LOCAL) { bq.x = ZERO + o8 + 3; bq.y = ZERO | 3; bq.z = ZERO | TAG_L; }
+			else                         { bq.x = ZERO + o8 + 3; bq.y = NEGV | 3; bq.z = ZERO | TAG_M; }                      // :619-624
 		}
 		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
+		int hot[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) hot[r] = r == cap_r ? 1 : 0;
 		int kbest = AT_NEG_INIT, tbest = 0;                                         // local
 		int capM = AT_NEG_INIT, capMj = 0, capL = AT_NEG_INIT, capLj = 0;           // fit
-		int gH = 0, gC = 0;                                                         // global
+		int gH = 0;                                                                 // global
 
 		// first boundary block of the stripe above
 		int4 pre = make_int4(0, 0, 0, 0);
@@ -253,27 +280,18 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
 
 		// `cap`: std::true_type in the pair's last stripe -- only there can a lane hold the row whose cells the
-		// end-cell search looks at; the other stripes run a body without those compares and selects
+		// end-cell search looks at; the other stripes run a body without it
 		auto step = [&](const uint32_t t, const bool checked, auto cap) {
 			constexpr bool CAP = decltype(cap)::value;
 			const int j = (int)t - lane;
-			int rM = __shfl_up_sync(0xffffffffu, sM, 1);
-			int rL = __shfl_up_sync(0xffffffffu, sL, 1);
-			int rH = __shfl_up_sync(0xffffffffu, sH, 1);
-			int rC = __shfl_up_sync(0xffffffffu, sC, 1);
-			if (lane == 0) {
-				if (stripe == 0) {      // matrix row 0 at column t
-					if (MODE == MODE_GLOBAL)     { rM = NEGV; rL = NEGV; rH = 8 * (o + e * j) + m8; rC = ST_UPP; }          // :437-441
-					else if (MODE == MODE_LOCAL) { rM = ZERO + o8; rL = ZERO; rH = ZERO + m8; rC = ST_LOW; }
-					else                         { rM = ZERO + o8; rL = NEGV; rH = ZERO + m8; rC = ST_MID; }                // :619-624
-				} else {
-					const int4 b = sm.cring[t & 63u];
-					rM = b.x; rL = b.y; rH = b.z; rC = b.w;
-				}
-			}
-			if (checked && t == 0) { rH = pH; rC = pC; }      // step 0 only primes the pipeline: keep H(row0, 0)
-			int D = pH, DC = pC;
-			pH = rH; pC = rC;
+			if (feed) bq = sm.cring[t & 63u];
+			const int rM = __shfl_up_sync(0xffffffffu, sM, 1) * nz + bq.x;
+			const int rL = __shfl_up_sync(0xffffffffu, sL, 1) * nz + bq.y;
+			int rH = __shfl_up_sync(0xffffffffu, sH, 1) * nz + bq.z;
+			if (MODE == MODE_GLOBAL) rH += b0E * (int)t;
+			if (checked && t == 0) rH = pH;                   // step 0 only primes the pipeline: keep H(row0, 0)
+			int D = pH;
+			pH = rH;
 			if (!checked || (j >= 1 && j <= (int)l2)) {
 				const uint32_t y = (uint32_t)(j - 1) + sh;
 				const uint32_t c = PROF ? (uint32_t)symmap_s[sm.rg.tring[y & 511u]] : (uint32_t)sm.rg.tring[y & 511u] << 16;
@@ -284,53 +302,35 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 					for (int r2 = 0; r2 < R / 2; ++r2) { const int2 v2 = pp[r2]; pw[2 * r2] = v2.x; pw[2 * r2 + 1] = v2.y; }
 				}
 				int jadd = 0;
-				if (JUMP) jadd = sm.rg.jring[y & 511u] ? AT_NEG : 8 * (a.jp - o);     // M[i][j-1] + jump, or barred (:659-665)
-				int Lup = rL, MoUp = rM, Mo = 0, Ln = 0, Hm = 0, code = 0;
+				if (JUMP) jadd = sm.rg.jring[y & 511u] ? cc.j_barred : cc.j_enter;       // M[i][j-1] + jump, or barred (:659-665)
+				int lup = rL, mo_up = rM;
+				int rowM = 0, rowL = 0;
 				const int kold = kbest;
+				CellOut<false> out;
 #pragma unroll
 				for (int r = 0; r < R; ++r) {
-					int Mraw;                                                     // H(i-1,j-1) + s
-					if (PROF) Mraw = D + pw[r];
-					else { const int tt = (int)min(ac[r] ^ c, mu8); Mraw = tt * nsg + D; }   // tt: 0 on a match, 8|m-u| otherwise
-					int Mn = Mraw, pm = DC;
-					if (MODE == MODE_LOCAL) { Mn = max(Mraw, ZERO); pm = DC | (int)min((uint32_t)(Mn - Mraw), 3u); }   // HOME (:825)
-					const int Lext = Lup + e8;
-					Ln = max(Lext, MoUp);
-					const int fL = (int)min((uint32_t)(Ln - Lext), 4u);           // gap opened only when strictly better (:456)
-					const int Un = __viaddmax_s32(Ul[r], e8, Mol[r]);
-					const int fU = (int)min((uint32_t)(Un - Mol[r]), 8u);         // gap extended only when strictly better (:460)
-					int Jn = 0, fJ = 0;
-					if (JUMP) {
-						const int ent = Mol[r] + jadd;
-						Jn = max(ent, Jl[r]);
-						fJ = (int)min((uint32_t)(Jn - ent), 1u);                  // stay in J only when strictly better (:660)
-					}
-					Mo = Mn + o8;
-					int H = __vimax3_s32(Ln, Mn, Un);
-					// first strictly greater in the order L, M, U (0 / 1 / 2): notL, notM are 0 or 3; L wins -> 0, M -> 3 & 1, U -> 3 & 2
-					code = (int)min((uint32_t)(H - Ln), 3u) & ((int)min((uint32_t)(H - Mn), 3u) ^ 1);
-					if (JUMP) { const int H4 = max(H, Jn); code = max(code, (int)min((uint32_t)(H4 - H), 3u)); H = H4; }
-					Hm = H + m8;
-					acc[r] = acc[r] * 16u + (uint32_t)(pm | fL) + (uint32_t)fU;
-					if (JUMP) accJ[r] = accJ[r] * 2u + (uint32_t)fJ;
-					if (MODE == MODE_LOCAL) kbest = __viaddmax_s32(Mn, crow[r], kbest);
-					if (MODE == MODE_FIT && CAP) {
-						if (r == cap_r && j < (int)l2) {                         // column l2 excluded (:677, :684)
-							if (Mn > capM) { capM = Mn; capMj = j; }
-							if (Ln > capL) { capL = Ln; capLj = j; }
-						}
-					}
-					if (MODE == MODE_GLOBAL && CAP) { if (r == cap_r && j == (int)l2) { gH = H; gC = code; } }
-					D = Hl[r]; DC = Cl[r];
-					Hl[r] = Hm; Cl[r] = code; Ul[r] = Un; Mol[r] = Mo; if (JUMP) Jl[r] = Jn;
-					Lup = Ln; MoUp = Mo;
+					int s8;                                                       // 8 s(i, j)
+					if (PROF) s8 = pw[r];
+					else { const int tt = (int)min(ac[r] ^ c, mu8); s8 = tt * nsg + m8; }   // tt: 0 on a match, 8|m-u| otherwise
+					D = cell_update<LOCAL, JUMP, false, true>(cc, st[r], D, s8, lup, mo_up, jadd, 16u, 2u, out);
+					lup = out.lk; mo_up = out.mo;
+					if (LOCAL) kbest = __viaddmax_s32(out.mk, crow[r], kbest);
+					if (MODE == MODE_FIT && CAP) { rowM += out.mk * hot[r]; rowL += out.lk * hot[r]; }      // one-hot pick of the pair's last row (FMA pipe)
+					if (MODE == MODE_GLOBAL && CAP) { if (r == cap_r && j == (int)l2) gH = out.h; }
 				}
-				sM = Mo; sL = Ln; sH = Hm; sC = code;
-				if (MODE == MODE_LOCAL) { if (kbest != kold) tbest = (int)t; }
-				if (lane == 31 && !last_stripe) sm.stage[(uint32_t)j & 63u] = make_int4(sM, sL, sH, sC);
+				sM = out.mo; sL = out.lk; sH = out.h;
+				if (MODE == MODE_FIT && CAP) {
+					if (cap_r >= 0 && j < (int)l2) {                              // column l2 excluded (:677, :684)
+						rowM &= ~7; rowL &= ~7;                                   // drop the tags: M and L are compared with each other at the end
+						if (rowM > capM) { capM = rowM; capMj = j; }
+						if (rowL > capL) { capL = rowL; capLj = j; }
+					}
+				}
+				if (LOCAL) { if (kbest != kold) tbest = (int)t; }
+				if (park) sm.stage[(uint32_t)j & 63u] = make_int4(sM, sL, sH, 0);
 			} else {
 #pragma unroll
-				for (int r = 0; r < R; ++r) { acc[r] *= 16u; if (JUMP) accJ[r] *= 2u; }
+				for (int r = 0; r < R; ++r) { st[r].x *= 16u; if (JUMP) st[r].xj *= 2u; }
 			}
 		};
 
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 				const uint32_t c = (tb >> 8) + 1u;
 				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
 			}
-			// two steps per loop body: 8 rows x 2 steps already is ~600 instructions; a fully unrolled pointer
+			// two steps per loop body: 8 rows x 2 steps already is ~400 instructions; a fully unrolled pointer
 			// word (8 steps) overflows the instruction cache (ncu: stall_no_instruction was the top stall)
 			if (tb >= 32u && tb + 7u <= l2) {
 				if (last_stripe) {
@@ -379,12 +379,12 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 			if (want_ptr && (tb >> 3) < G) {
 				uint32_t *w = ptr + ((size_t)(stripe * G + (tb >> 3)) * 32 + lane) * R;
 #pragma unroll
-				for (int r = 0; r < R; ++r) w[r] = acc[r];
+				for (int r = 0; r < R; ++r) w[r] = ptr_word(st[r].x);
 			}
 			if (JUMP && want_ptr && (tb & 31u) == 24u && (tb >> 5) < GJ) {
 				uint32_t *w = ptrJ + ((size_t)(stripe * GJ + (tb >> 5)) * 32 + lane) * R;
 #pragma unroll
-				for (int r = 0; r < R; ++r) w[r] = accJ[r];
+				for (int r = 0; r < R; ++r) w[r] = jump_word(st[r].xj);
 			}
 		}
 		__syncwarp();
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 		}
 
 		// ---- end cell (reference: :466-469 global, :673-690 fit, running max :830-833 local) ----
-		if (MODE == MODE_LOCAL) {
+		if (LOCAL) {
 			int sc = -1, row = 0x7fffffff, col = 0;
 			if (kbest >= 0) { sc = kbest >> 3; row = (int)row0 + (7 - (kbest & 7)) + 1; col = tbest - lane; }
 #pragma unroll
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_affine(const WaveA
 		} else if (last_stripe) {
 			const int owner = (int)(((l1 - 1) % RPP) / R);
 			if (lane == owner) {
-				if (MODE == MODE_GLOBAL) { a.score[p] = gH >> 3; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = (uint8_t)gC; }
+				if (MODE == MODE_GLOBAL) { a.score[p] = gH >> 3; a.end_i[p] = l1; a.end_j[p] = l2; a.end_state[p] = (uint8_t)(3 - (gH & 3)); }
 				else {
 					const bool useL = capL > capM;            // L replaces M only when strictly greater (:685)
 					a.score[p] = (useL ? capL : capM) >> 3; a.end_i[p] = l1; a.end_j[p] = useL ? capLj : capMj;

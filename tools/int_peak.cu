@@ -14,11 +14,11 @@
 #define ITERS 4096
 #define ILP 8
 
-enum { OP_IADD, OP_MAX, OP_ADDMAX, OP_MAX3, OP_LOP3, OP_IMAD, OP_MAX16, OP_ADDMAX16, OP_MAX3_16, OP_MIX_1_1, OP_MIX_2_1, OP_MIX16_1_1, OP_SHFL, OP_LDS, OP_N };
+enum { OP_IADD, OP_MAX, OP_ADDMAX, OP_MAX3, OP_LOP3, OP_IMAD, OP_MAX16, OP_ADDMAX16, OP_MAX3_16, OP_MIX_1_1, OP_MIX_2_1, OP_MIX16_1_1, OP_SHFL, OP_LDS, OP_CELL_MIX, OP_N };
 static const char *NAMES[] = {"IADD3 (a+b)", "VIMNMX (max s32)", "VIADDMNMX (max(a+b,c))", "VIMNMX3 (max3)", "LOP3 ((a&b)|c)",
                               "IMAD (a*b+c)", "VIMNMX.U16x2", "VIADDMNMX.U16x2", "VIMNMX3.U16x2", "mix VIADDMNMX : IMAD 1:1",
-                              "mix (VIADDMNMX,LOP3) : IMAD 2:1", "mix VIADDMNMX.U16x2 : IMAD 1:1", "SHFL.UP", "LDS.32"};
-static const int OPS_PER_SLOT[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 2, 1, 1};     // instructions one loop slot issues
+                              "mix (VIADDMNMX,LOP3) : IMAD 2:1", "mix VIADDMNMX.U16x2 : IMAD 1:1", "SHFL.UP", "LDS.32", "packed cell mix 8 ALU : 7 IMAD"};
+static const int OPS_PER_SLOT[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 2, 1, 1, 15};     // instructions one loop slot issues
 
 template <int OP>
 __global__ void k(int *out, int a0, int b0, long long *clk)
@@ -48,7 +48,27 @@ __global__ void k(int *out, int a0, int b0, long long *clk)
 			else if (OP == OP_MIX_1_1) { x[i] = __viaddmax_s32(x[i], b, c); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c)); }
 			else if (OP == OP_MIX_2_1) { x[i] = __viaddmax_s32(x[i], b, c); asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(x[i]) : "r"(b), "r"(c));
 			                             asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c)); }
-			else if (OP == OP_MIX16_1_1) { x[i] = (int)__viaddmax_u16x2((unsigned)x[i], (unsigned)b, (unsigned)c); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c)); }
+			else if (OP == OP_MIX16_1_1) {      // volatile statements keep their order: ALU and FMA instructions alternate in the SASS
+				asm volatile("{.reg .b32 t1;\n\tadd.u16x2 t1, %0, %1;\n\tmax.u16x2 %0, t1, %2;}" : "+r"(x[i]) : "r"(b), "r"(c));
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+			}
+			else if (OP == OP_CELL_MIX) {       // the instruction mix of one packed cell of at_cell.cuh: 5 max-type + 3 LOP3 on the ALU pipe, 7 IMAD on the FMA pipe
+				asm volatile("{.reg .b32 t1;\n\tadd.u16x2 t1, %0, %1;\n\tmax.u16x2 %0, t1, %2;}" : "+r"(x[i]) : "r"(b), "r"(c));
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+				asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(x[i]) : "r"(b), "r"(c));
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+				asm volatile("{.reg .b32 t1;\n\tadd.u16x2 t1, %0, %1;\n\tmax.u16x2 %0, t1, %2;}" : "+r"(x[i]) : "r"(b), "r"(c));
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+				asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(x[i]) : "r"(b), "r"(c));
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+				asm volatile("{.reg .b32 t1;\n\tadd.u16x2 t1, %0, %1;\n\tmax.u16x2 %0, t1, %2;}" : "+r"(x[i]) : "r"(b), "r"(c));
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+				asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(x[i]) : "r"(b), "r"(c));
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+				x[i] = (int)__vimax3_u16x2((unsigned)x[i], (unsigned)b, (unsigned)c);
+				asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(c));
+				asm volatile("{.reg .b32 t1;\n\tadd.u16x2 t1, %0, %1;\n\tmax.u16x2 %0, t1, %2;}" : "+r"(x[i]) : "r"(b), "r"(c));
+			}
 			else if (OP == OP_SHFL) x[i] = __shfl_up_sync(0xffffffffu, x[i], 1);
 			else if (OP == OP_LDS) x[i] = sh[x[i] & 1023];
 		}
@@ -98,6 +118,7 @@ int main()
 	run<OP_MIX16_1_1>(p.multiProcessorCount, d_out, d_clk);
 	run<OP_SHFL>(p.multiProcessorCount, d_out, d_clk);
 	run<OP_LDS>(p.multiProcessorCount, d_out, d_clk);
+	run<OP_CELL_MIX>(p.multiProcessorCount, d_out, d_clk);
 	cudaError_t e = cudaDeviceSynchronize();
 	printf("status: %s\n", cudaGetErrorString(e));
 	return e != cudaSuccess;
