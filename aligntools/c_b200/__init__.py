@@ -138,9 +138,11 @@ class Opt:
     j: int = -10
     jump: bool = False          # `-s`
     sites: list = field(default_factory=list)
+    whitelist: bool = False     # jump state with the site list as a WHITELIST (at_params.jump == 2): entering J only
+                                # on the listed indices, as the comment at src/alignment.h:542-544 describes
 
     def c(self):
-        return _Params(self.m, self.u, self.o, self.e, self.j, int(self.jump))
+        return _Params(self.m, self.u, self.o, self.e, self.j, 2 if (self.jump and self.whitelist) else int(self.jump))
 
 
 @dataclass

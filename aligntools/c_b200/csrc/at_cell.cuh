@@ -220,4 +220,37 @@ AT_HD typename Lanes<PACKED>::T cell_update(const CellConst<PACKED> &c, RowState
 AT_HD uint32_t ptr_word(uint32_t x) { return x + AT_PTR_BIAS; }
 AT_HD uint32_t jump_word(uint32_t xj) { return ~xj; }
 
+// ------------------------------------------------------------------------------------------------
+// Single-plane cell (overlap: max-plus with a linear gap, src/alignment.h:940-949), int32 lanes.
+// Values are kept x4 and every cell carries A = 4 M + 4 o (what its right and lower neighbours add anyway).
+// Tags in the two spare bits reproduce max5's order LEFT, DIAGONAL, RIGHT (:944-947, first strictly greater):
+//     LEFT 2, DIAGONAL 1, RIGHT 0;   pointer code (K3: bit 1 RIGHT, bit 0 DIAGONAL) = 2 - tag.
+// A cell hands on its value in two forms: `a` (tag 0: the RIGHT candidate of the row below) and `a2` = a + 2 (its own
+// LEFT candidate one column later, and the diagonal input of the row below, whose profile word carries - 1).
+//     vt = max3(a2(i, j-1), a2(i-1, j-1) + 4 (s - o) - 1, a(i-1, j))        one VIMNMX3: value + argmax
+//     x  = 4 x + (vt - (vt & ~3))                                           the 2-bit pointers: word = 0xAAAAAAAA - x
+// ------------------------------------------------------------------------------------------------
+#define AT_NEGL (-(1 << 30))       // -inf stand-in of the single-plane kernel (scores x4 stay below 2^29)
+#define AT_LIN_BIAS 0xAAAAAAAAu    // 2 per 2-bit field
+
+struct LinRow { int a2; uint32_t x; };      // A(i, j-1) + 2 and the pointer accumulator of one row
+
+// d2: a2(i-1, j-1); pw: 4 (s(i, j) - o) - 1; a_up: a(i-1, j); gap = 4 o.  Returns a(i, j); st.a2 is replaced by
+// a2(i, j) and the OLD st.a2 -- the diagonal input of the row below -- comes back through d2_next.
+AT_HD int lin_update(LinRow &st, const int d2, const int pw, const int a_up, const int gap, int &d2_next)
+{
+	const int diag = d2 + pw;
+#ifdef __CUDA_ARCH__
+	const int vt = __vimax3_s32(st.a2, diag, a_up);
+#else
+	int vt = st.a2 > diag ? st.a2 : diag; vt = vt > a_up ? vt : a_up;
+#endif
+	const int vk = opaque<int>(vt & ~3);
+	st.x = st.x * 4u + ((uint32_t)vt - (uint32_t)vk);
+	d2_next = st.a2;
+	st.a2 = vk + (gap + 2);
+	return vk + gap;
+}
+AT_HD uint32_t lin_word(uint32_t x) { return AT_LIN_BIAS - x; }
+
 }  // namespace atb2

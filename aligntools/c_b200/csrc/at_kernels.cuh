@@ -310,15 +310,17 @@ __global__ void __launch_bounds__(256) at_symbol_set(const uint8_t *bytes, uint6
 }
 
 // fit+jump: expand the per-pair blacklists into a byte mask aligned with the target bytes.
+// `mark`: 1 = the listed indices are barred (the reference's behaviour), 0 = they are the only ones allowed (whitelist:
+// the mask was preset to ones).
 __global__ void at_build_jmask(const int32_t *sites, const uint64_t *site_off, const uint64_t *t_off,
-                               const uint32_t *t_len, uint32_t n_pairs, uint8_t *jmask)
+                               const uint32_t *t_len, uint32_t n_pairs, uint8_t *jmask, uint8_t mark)
 {
 	const uint32_t p = blockIdx.x;
 	if (p >= n_pairs) return;
 	const uint64_t lo = site_off[p], hi = site_off[p + 1];
 	for (uint64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
 		const int32_t s = sites[k];
-		if (s >= 0 && (uint32_t)s < t_len[p]) jmask[t_off[p] + s] = 1;
+		if (s >= 0 && (uint32_t)s < t_len[p]) jmask[t_off[p] + s] = mark;
 	}
 }
 

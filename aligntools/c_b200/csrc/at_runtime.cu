@@ -418,8 +418,11 @@ static int build_jump_mask(at_batch *b, Shard &s, const at_batch_input *in)
 	at_handle *h = b->h;
 	cudaStream_t st = s.stream;
 	const uint32_t n = s.n;
+	// params.jump == 2 (junction WHITELIST, the semantics of the comment at src/alignment.h:542-544): entering J is
+	// barred everywhere except on the listed indices -- the mask starts as all ones and the sites clear it
+	const bool whitelist = b->prm.jump == 2;
 	CU(h, s.d_jmask.alloc(s.d_t.n));
-	CU(h, cudaMemsetAsync(s.d_jmask.p, 0, s.d_t.n, st));
+	CU(h, cudaMemsetAsync(s.d_jmask.p, whitelist ? 1 : 0, s.d_t.n, st));
 	if (!in->sites || !in->site_off) return AT_OK;
 	const uint64_t lo = in->site_off[s.p0], hi = in->site_off[s.p1];
 	std::vector<uint64_t> so(n + 1);
@@ -427,7 +430,7 @@ static int build_jump_mask(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, s.d_sites.alloc(hi - lo + 1)); CU(h, s.d_site_off.alloc(n + 1));
 	if (hi > lo) CU(h, cudaMemcpyAsync(s.d_sites.p, in->sites + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
 	CU(h, cudaMemcpyAsync(s.d_site_off.p, so.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-	at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, s.d_t_off.p, s.d_t_len.p, n, s.d_jmask.p);
+	at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, s.d_t_off.p, s.d_t_len.p, n, s.d_jmask.p, whitelist ? 0 : 1);
 	CU(h, cudaGetLastError());
 	h->launches++;
 	CU(h, cudaStreamSynchronize(st));

@@ -33,7 +33,6 @@ namespace atb2 {
 constexpr int AT_WAVE_UNROLL_AFFINE = 2;     // steps per loop body (instruction-cache footprint, see the loops)
 constexpr int AT_WAVE_UNROLL_OVERLAP = 4, AT_WAVE_UNROLL_EDIT = 8;
 #define AT_PROG_DONE 0xffffffffu
-#define AT_NEGL (-(1 << 30))       // -inf stand-in of the single-plane kernel (scores x4 stay below 2^29)
 
 struct WaveTask { uint32_t pair, stripe; };
 
@@ -440,15 +439,16 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, 4) at_wave_affine(const Wa
 // Single-plane kernel: overlap (max-plus, linear gap, 2-bit pointers) and edit distance
 // (min-plus, unit gaps, score only), int32 lanes, R = 1..8 rows per lane.
 //
-// Overlap keeps scores x4 and carries A = 4*M + 4*o (what the left and the upper neighbour
-// add anyway); the diagonal input is A + 4(m-o) minus the substitution penalty.  The 2-bit
-// pointer is two difference flags: bit 0 = diagonal beat left, bit 1 = up beat both
-// (reference order LEFT, DIAGONAL, RIGHT with first-strictly-greater ties, :944-947).
+// Overlap runs lin_update() of at_cell.cuh: scores x4, every cell carries A = 4*M + 4*o, the argmax of the one
+// VIMNMX3 rides in the two spare bits (LEFT 2, DIAGONAL 1, RIGHT 0: the reference's order with
+// first-strictly-greater ties, :944-947) and the 2-bit pointers are accumulated on the FMA pipe.
+// Edit distance is min3 (:280-286) with one VIADDMNMX and one VIMNMX per cell.
 // =====================================================================================
 // PROF (targets of the shard use at most four distinct bytes): the substitution term comes from a per-warp
-// query profile in shared memory, prof[code][lane][r] = 0 on a match, -+penalty otherwise, as in K1 -- one
-// 64-bit LDS per two rows and an add instead of xor / min / multiply-add per cell (the ALU pipe is this
-// kernel's limiter); a.symmap maps target bytes to codes.
+// query profile in shared memory, prof[code][lane][r] (overlap: 4 (s - o) - 1, the diagonal's tag included; edit: 0 on a
+// match, the mismatch cost otherwise), as in K1 -- one 64-bit LDS per two rows; a.symmap maps target bytes to codes.
+// Lane 0's upper neighbour (matrix row 0, or the stripe above through the boundary ring) enters through a
+// multiply-add with a 0/1 lane mask, not a branch.
 template <int MODE, int R, bool PROF>
 __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveArgs a)
 {
@@ -469,10 +469,12 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 	// overlap: S = 4, step cost o, substitution m / u; edit: S = 1, step cost +1, substitution 0 / u
 	const int S = OV ? 4 : 1;
 	const int gap = OV ? S * a.o : 1;
-	const int dm = OV ? S * (a.m - a.o) : 0;                          // carried value -> diagonal input on a match
+	const int pw_match = OV ? S * (a.m - a.o) - 1 : 0;               // substitution term of a match (overlap: carried value -> tagged diagonal candidate)
 	const uint32_t pen = OV ? (uint32_t)(S * (a.m >= a.u ? a.m - a.u : a.u - a.m)) : (uint32_t)(a.u >= 0 ? a.u : -a.u);
 	const int nsg = OV ? (a.m >= a.u ? -1 : 1) : (a.u >= 0 ? 1 : -1);
 	const bool want_ptr = OV && a.want_ptr != 0;
+	int nz = lane ? 1 : 0;                                            // lane 0 takes the row above the stripe instead of a neighbour
+	asm volatile("" : "+r"(nz));                                      // opaque: keep x * nz + b a multiply-add (FMA pipe), not a SEL
 
 	for (;;) {
 		uint32_t job = 0;
@@ -501,32 +503,43 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		const uint64_t tag_out = (uint64_t)(stripe + 1u) << 32;
 		const uint32_t tag_in = stripe;                                   // the predecessor's (stripe - 1) + 1
 		const uint32_t row0 = stripe * RPP + lane * R;
+		const bool feed = lane == 0 && stripe > 0;                        // this lane reads the boundary ring
+		const bool park = lane == 31 && !last_stripe;                     // this lane parks its last row for the next stripe
 
 		__syncwarp();
 		if (n_tiles > 0) ring_issue<false>(sm.rg, tbase16, nullptr, 0, lane);
 		if (n_tiles > 1) ring_issue<false>(sm.rg, tbase16, nullptr, 1, lane);
 
-		// carried value V: overlap 4*M + 4*o, edit M.  Column 0: M[i][0] = 0 (:938) | i (:301)
-		uint32_t ac[R], acc[R];
+		// carried value: overlap a = 4*M + 4*o (LinRow keeps a + 2), edit M.  Column 0: M[i][0] = 0 (:938) | i (:301)
+		uint32_t ac[R];
+		LinRow stl[R];
 		int Vl[R];
 #pragma unroll
 		for (int r = 0; r < R; ++r) {
 			const uint32_t ri = row0 + r;
 			ac[r] = ri < l1 ? ((uint32_t)q[ri] << 16) : 0x4u;
-			Vl[r] = OV ? gap : (int)ri + 1;
-			acc[r] = 0;
+			Vl[r] = (int)ri + 1;
+			stl[r].a2 = gap + 2; stl[r].x = 0;
 			if (PROF) {
 				const uint32_t qa = ri < l1 ? (uint32_t)q[ri] : 0x100u;
 #pragma unroll
-				for (int c = 0; c < 4; ++c) sm.prof[c][lane][r] = qa == ((a.syms >> (8 * c)) & 255u) ? 0 : (int)pen * nsg;
+				for (int c = 0; c < 4; ++c) sm.prof[c][lane][r] = pw_match + (qa == ((a.syms >> (8 * c)) & 255u) ? 0 : (int)pen * nsg);
 			}
 		}
 		if (PROF) __syncwarp();
-		int sV = Vl[R - 1];
+		int sV = OV ? gap : Vl[R - 1];
 		int pD = 0;                                               // diagonal input of the lane's first row (set at the step with j = 0)
-		const int col0 = OV ? gap : (int)row0;                    // V(row0, 0): the row above this lane's strip
+		const int col0 = OV ? gap : (int)row0;                    // value of the row above this lane's strip at column 0
+		const int dadd = OV ? 2 : 0;                              // overlap: the diagonal input is a + 2
 		const int cap_r = (last_stripe && lane == (int)(((l1 - 1) % RPP) / R)) ? (int)((l1 - 1) % R) : -1;
+		int hot[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) hot[r] = r == cap_r ? 1 : 0;
 		int capV = OV ? gap : 0, capJ = 0;                        // overlap: M[l1][0] = 0 seeds the search (:954-959)
+		// what lane 0 adds instead of a neighbour's row (zero in every other lane): matrix row 0 in the first stripe
+		// (overlap: -inf, :937; edit: j, :302), the boundary ring's element otherwise (loaded per step by lane 0 alone)
+		int bq = 0, b0E = 0;
+		if (lane == 0 && stripe == 0) { if (OV) bq = AT_NEGL; else b0E = 1; }
 
 		uint64_t pre = 0;
 		if (stripe) {
@@ -541,14 +554,12 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		auto step = [&](const uint32_t t, const bool checked, auto cap) {
 			constexpr bool CAP = decltype(cap)::value;
 			const int j = (int)t - lane;
-			int rV = __shfl_up_sync(0xffffffffu, sV, 1);
-			if (lane == 0) {
-				if (stripe == 0) rV = OV ? AT_NEGL : (int)t;                      // M[0][j] = -inf (:937) | j (:302)
-				else rV = sm.cring[t & 63u];
-				if (checked && t == 0) rV = col0;
-			}
+			if (feed) bq = sm.cring[t & 63u];
+			int rV = __shfl_up_sync(0xffffffffu, sV, 1) * nz + bq;
+			if (!OV) rV += b0E * (int)t;
+			if (checked && t == 0) rV = col0;
 			int D = pD;
-			pD = rV + dm;
+			pD = rV + dadd;
 			if (!checked || (j >= 1 && j <= (int)l2)) {
 				const uint32_t y = (uint32_t)(j - 1) + sh;
 				const uint32_t c = PROF ? (uint32_t)symmap_s[sm.rg.tring[y & 511u]] : (uint32_t)sm.rg.tring[y & 511u] << 16;
@@ -558,37 +569,34 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 #pragma unroll
 					for (int r2 = 0; r2 < (R + 1) / 2; ++r2) { const int2 v2 = pp[r2]; pw[2 * r2] = v2.x; pw[2 * r2 + 1] = v2.y; }
 				}
-				int Vup = rV, v = 0;
+				int Vup = rV, v = 0, rowV = 0;
 #pragma unroll
 				for (int r = 0; r < R; ++r) {
-					int diag;
-					if (PROF) diag = D + pw[r];
-					else { const int tt = (int)min(ac[r] ^ c, pen); diag = tt * nsg + D; }   // tt: 0 on a match
-					D = Vl[r] + dm;
+					int sub;                                                      // substitution term
+					if (PROF) sub = pw[r];
+					else { const int tt = (int)min(ac[r] ^ c, pen); sub = tt * nsg + pw_match; }   // tt: 0 on a match
 					if (OV) {
-						const int v1 = max(Vl[r], diag);                          // LEFT keeps ties (:944)
-						const int vm = max(v1, Vup);
-						const uint32_t f1 = min((uint32_t)(v1 - Vl[r]), 1u);      // DIAGONAL strictly greater
-						const uint32_t f2 = min((uint32_t)(vm - v1), 2u);         // RIGHT strictly greater
-						acc[r] = acc[r] * 4u + f1 + f2;
-						v = vm + gap;
+						int dn;
+						v = lin_update(stl[r], D, sub, Vup, gap, dn);
+						D = dn;
 					} else {
+						const int diag = D + sub;
+						D = Vl[r];
 						v = __viaddmin_s32(min(Vl[r], Vup), 1, diag);             // min3 (:280-286)
+						Vl[r] = v;
 					}
-					Vl[r] = v; Vup = v;
+					Vup = v;
+					if (CAP) rowV += v * hot[r];                                  // one-hot pick of the pair's last row (FMA pipe)
 				}
 				sV = v;
-				if (lane == 31 && !last_stripe) sm.stage[(uint32_t)j & 63u] = sV;
+				if (park) sm.stage[(uint32_t)j & 63u] = sV;
 				if (CAP && cap_r >= 0) {                                          // the pair's last row lives in this lane
-					int vc = Vl[0];
-#pragma unroll
-					for (int r = 1; r < R; ++r) if (cap_r == r) vc = Vl[r];
-					if (OV) { if (j < (int)l2 && vc > capV) { capV = vc; capJ = j; } }   // column l2 excluded (:955)
-					else if (j == (int)l2) capV = vc;
+					if (OV) { if (j < (int)l2 && rowV > capV) { capV = rowV; capJ = j; } }   // column l2 excluded (:955)
+					else if (j == (int)l2) capV = rowV;
 				}
 			} else if (OV) {
 #pragma unroll
-				for (int r = 0; r < R; ++r) acc[r] *= 4u;
+				for (int r = 0; r < R; ++r) stl[r].x *= 4u;
 			}
 		};
 
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 			if (want_ptr && (tb >> 4) < G) {
 				uint32_t *w = ptr + ((size_t)(stripe * G + (tb >> 4)) * 32 + lane) * R;
 #pragma unroll
-				for (int r = 0; r < R; ++r) w[r] = acc[r];
+				for (int r = 0; r < R; ++r) w[r] = lin_word(stl[r].x);
 			}
 		}
 		__syncwarp();

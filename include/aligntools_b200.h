@@ -61,7 +61,10 @@ typedef struct at_params {
 	int32_t o;      /* gap open           [-5]  */
 	int32_t e;      /* gap extension      [-1]  */
 	int32_t j;      /* jump penalty       [-10] */
-	int32_t jump;   /* 1 = `-s` given (the reference stores this as opt->s == true == 0) */
+	int32_t jump;   /* 0 = no jump state; 1 = `-s` given (the reference stores this as opt->s == true == 0): the site
+	                   list is a BLACKLIST, bit-exact with the reference; 2 = jump state with the
+	                   site list as a WHITELIST -- entering J only on the listed target indices, the semantics
+	                   the reference's own comments describe (src/alignment.h:542-544) but do not implement */
 } at_params;
 
 void        at_default_params(at_params *p);

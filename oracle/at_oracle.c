@@ -75,12 +75,16 @@ static void reverse_bytes(char *s, size_t n)
 /* blacklist test of :659 -- isvalueinarray() returns the enum `true` (== 0) when the
  * value IS found, so `if (isvalueinarray(...))` takes the "may enter J" branch exactly
  * when j-1 is NOT listed. */
-static uint8_t *build_site_mask(const int *sites, size_t n_sites, size_t l2)
+static uint8_t *build_site_mask(const int *sites, size_t n_sites, size_t l2, int whitelist)
 {
 	uint8_t *mask = (uint8_t *)calloc(l2 + 1, 1);
 	size_t k;
+	/* jump == 2: the semantics the reference's comments describe (:542-544, "we allow pointer move from M to J only
+	 * at given positions on s2") but its inverted `bool` does not implement: entering J is barred everywhere
+	 * EXCEPT on the listed target indices.  Equivalent to the blacklist mode run on the complement of the list. */
+	if (whitelist) memset(mask, 1, l2 + 1);
 	for (k = 0; k < n_sites; k++)
-		if (sites[k] >= 0 && (size_t)sites[k] < l2) mask[sites[k]] = 1;
+		if (sites[k] >= 0 && (size_t)sites[k] < l2) mask[sites[k]] = whitelist ? 0 : 1;
 	return mask;
 }
 
@@ -95,7 +99,7 @@ static int affine_align(int mode, const uint8_t *s1, size_t l1, const uint8_t *s
 	size_t W = l2 + 1, i, j;
 	uint8_t *P = (uint8_t *)calloc((l1 + 1) * W, 1);
 	uint8_t *PJ = (mode == AT_FIT && jump) ? (uint8_t *)calloc((l1 + 1) * W, 1) : NULL;
-	uint8_t *smask = (mode == AT_FIT && jump) ? build_site_mask(sites, n_sites, l2) : NULL;
+	uint8_t *smask = (mode == AT_FIT && jump) ? build_site_mask(sites, n_sites, l2, jump == 2) : NULL;
 	int64_t *buf = (int64_t *)malloc(sizeof(int64_t) * 8 * W);
 	int64_t *Mp = buf, *Lp = buf + W, *Up = buf + 2 * W, *Jp = buf + 3 * W;
 	int64_t *Mc = buf + 4 * W, *Lc = buf + 5 * W, *Uc = buf + 6 * W, *Jc = buf + 7 * W;

@@ -133,6 +133,46 @@ static int walk(const PairIO &p, int mode, int jump, char *ops, int *beg_i, int 
 	return n;
 }
 
+
+// ---- overlap (single plane, lin_update) ----
+static void fill_overlap(PairIO &p, int m, int u, int o)
+{
+	const int l1 = p.l1, l2 = p.l2, gap = 4 * o;
+	p.nib.assign((size_t)(l1 + 1) * (l2 + 1), 0xff);
+	std::vector<LinRow> row(l1 + 1);
+	for (int i = 1; i <= l1; ++i) { row[i].a2 = gap + 2; row[i].x = 0; }      // M[i][0] = 0 (:938): A = 4 o
+	long capV = gap; int capJ = 0;                                            // M[l1][0] = 0 seeds the search (:954-959)
+	for (int j = 1; j <= l2; ++j) {
+		int d2 = (j == 1 ? gap : AT_NEGL) + 2;                                // A(0, j-1): M[0][0] = 0, M[0][j] = -inf (:937)
+		int a_up = AT_NEGL;
+		for (int i = 1; i <= l1; ++i) {
+			const int s = p.s1[i - 1] == p.s2[j - 1] ? m : u;
+			int d2n;
+			a_up = lin_update(row[i], d2, 4 * (s - o) - 1, a_up, gap, d2n);
+			d2 = d2n;
+			p.nib[(size_t)i * (l2 + 1) + j] = (uint8_t)(lin_word(row[i].x) & 3u);
+			if (i == l1 && j < l2 && a_up > capV) { capV = a_up; capJ = j; }  // column l2 excluded (:955)
+		}
+	}
+	p.score = (int)((capV - gap) / 4); p.end_i = l1; p.end_j = capJ; p.end_state = ST_MID;
+}
+
+static int walk_overlap(const PairIO &p, char *ops, int *beg_i, int *beg_j)
+{
+	int i = p.end_i, j = p.end_j, n = 0;
+	std::vector<char> rev;
+	while (j > 0) {                                                           // :899
+		if (i == 0) break;
+		const uint32_t c = p.nib[(size_t)i * (p.l2 + 1) + j];
+		if (c & 2u)      { --i; rev.push_back('I'); }
+		else if (c & 1u) { --i; --j; rev.push_back('M'); }
+		else             { --j; rev.push_back('D'); }
+	}
+	*beg_i = i; *beg_j = j;
+	for (size_t k = rev.size(); k-- > 0;) ops[n++] = rev[k];
+	return n;
+}
+
 // One pair (packed = 0) or two pairs sharing l2 (packed = 1; local only).  ops_* must hold l1 + l2 bytes.
 // out[h] = {score, end_i, end_j, end_state, beg_i, beg_j, n_ops}
 extern "C" int cell_model_run(int mode, int jump, int packed, const uint8_t *s1a, int l1a, const uint8_t *s1b, int l1b,
@@ -142,6 +182,13 @@ extern "C" int cell_model_run(int mode, int jump, int packed, const uint8_t *s1a
 	PairIO pp[2];
 	pp[0].s1 = s1a; pp[0].l1 = l1a; pp[0].s2 = s2a; pp[0].l2 = l2; pp[0].sites = sites; pp[0].n_sites = n_sites;
 	pp[1].s1 = s1b; pp[1].l1 = l1b; pp[1].s2 = s2b; pp[1].l2 = l2; pp[1].sites = sites; pp[1].n_sites = n_sites;
+	if (mode == 3) {
+		fill_overlap(pp[0], m, u, o);
+		int bi = 0, bj = 0;
+		const int n = walk_overlap(pp[0], ops_a, &bi, &bj);
+		out[0] = pp[0].score; out[1] = pp[0].end_i; out[2] = pp[0].end_j; out[3] = pp[0].end_state; out[4] = bi; out[5] = bj; out[6] = n;
+		return 0;
+	}
 	if (packed) {
 		if (mode != MODE_LOCAL || jump) return -1;
 		fill<MODE_LOCAL, false, true>(pp, m, u, o, e, jp, 0);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_build", "libcell_model.so")
 SRC = os.path.join(HERE, "cell_model.cpp")
 HDR = os.path.join(HERE, "..", "aligntools", "c_b200", "csrc", "at_cell.cuh")
-MODES = {"global": 0, "local": 1, "fit": 2}
+MODES = {"global": 0, "local": 1, "fit": 2, "overlap": 3}
 
 
 @pytest.fixture(scope="module")
@@ -104,3 +104,20 @@ def test_packed_lanes_vs_oracle(model, oracle_mod):
             assert got[h]["score"] == ref.score, (k, h, prm, s1, s2)
             assert got[h]["end"] == tuple(ref.coords[:2]) and got[h]["beg"] == tuple(ref.coords[2:]), (k, h, prm)
             assert got[h]["ops"] == ref.ops, (k, h, prm, s1, s2)
+
+
+def test_overlap_cell_vs_oracle(model, oracle_mod):
+    """Single-plane cell (lin_update): tags LEFT 2 / DIAGONAL 1 / RIGHT 0, 2-bit pointers as 0xAAAAAAAA - x."""
+    rng = random.Random(5)
+    for k in range(900):
+        l1, l2 = rng.randint(1, 90), rng.randint(1, 90)
+        s1 = bytes(rng.choice(b"ACGT") for _ in range(l1))
+        ov = rng.randint(0, min(l1, l2))
+        s2 = bytes(c if rng.random() > 0.1 else rng.choice(b"ACGT") for c in s1[l1 - ov:]) + bytes(rng.choice(b"ACGT") for _ in range(l2 - ov))
+        prm = rand_params(rng, flipped=(k % 4 == 3))
+        p = oracle_mod.Params(prm["m"], prm["u"], prm["o"], prm["e"], prm["j"], False)
+        ref = oracle_mod.port_align("overlap", s1, s2, p)
+        got = run_model(model, "overlap", False, False, s1, s1, s2, s2, prm, None)[0]
+        assert got["score"] == ref.score, (k, prm, s1, s2)
+        assert got["end"] == tuple(ref.coords[:2]) and got["beg"] == tuple(ref.coords[2:]), (k, prm, s1, s2)
+        assert got["ops"].replace(b"N", b"D") == ref.ops, (k, prm, s1, s2)

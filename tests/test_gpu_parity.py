@@ -411,3 +411,39 @@ def test_config2_full_size_checksums(A, aligner):
                                cigar_cap=gold["cigar_ops"] + 16)
     assert np.array_equal(one.score, res.score) and np.array_equal(one.cigar_off, res.cigar_off)
     assert np.array_equal(one.cigar[:gold["cigar_ops"]], ops)
+
+
+def test_junction_whitelist_mode(A, aligner, oracle_mod):
+    """at_params.jump == 2 -- entering the jump state only ON the listed target indices (the
+    semantics of the comment at src/alignment.h:542-544) -- on K1 (short reads) and K2 (multi-stripe reads) against
+    the oracle's restatement, which tests/test_oracle.py pins on the compiled reference."""
+    rng = random.Random(2468)
+    q, t, ss, so = [], [], [], [0]
+    for k in range(120):
+        l2 = rng.randint(40, 300) if k < 100 else rng.randint(1500, 4000)
+        s2 = bytes(rng.choice(b"ACGT") for _ in range(l2))
+        a, b = sorted(rng.sample(range(10, l2 - 10), 2))
+        ex = rng.randint(5, 120) if k < 100 else rng.randint(200, 700)
+        s1 = (s2[max(0, a - ex):a] + s2[b:b + ex]) or b"A"
+        s1 = bytes(c if rng.random() > 0.04 else rng.choice(b"ACGT") for c in s1)
+        q.append(s1); t.append(s2)
+        ss += sorted(set([a, b - 1, b] + [rng.randrange(l2) for _ in range(rng.choice([0, 3]))])); so.append(len(ss))
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    sites = np.array(ss + [0], dtype=np.int32); site_off = np.array(so, dtype=np.uint64)
+    prm = dict(m=1, u=-2, o=-5, e=-1, j=-6)
+    ref = oracle_mod.port_batch("fit", oracle_mod.Params(**prm, jump=2), qb, qo, ql, tb, to, tl, sites, site_off, want_aln=True, want_ops=True, threads=4)
+    b = aligner.batch("fit", A.Opt(**prm, jump=True, whitelist=True), qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off)
+    b.run()
+    res = b.fetch()
+    b.free()
+    assert np.array_equal(res.score.astype(np.int64), ref.score)
+    n_jump = 0
+    for k in range(len(q)):
+        assert res.aln(k) == ref.aln(k), k
+        assert res.cigar_string(k) == rle(ref.op(k)), k
+        n_jump += "N" in res.cigar_string(k)
+    assert n_jump > 30
+    # and the same list as a blacklist gives different alignments (the modes are not confused)
+    res_b = aligner.align("fit", q[:40], t[:40], A.Opt(**prm, jump=True), sites=[ss[so[k]:so[k + 1]] for k in range(40)])
+    assert any(res_b.aln(k) != res.aln(k) for k in range(40))

@@ -176,3 +176,27 @@ def test_port_20kbp_vs_reference(oracle_mod, mode):
         assert len(a.r1) > 10000
     if mode == "fitjump":
         assert a.ops.count(b"N") > 1000
+
+
+def test_port_whitelist_mode_is_blacklist_of_the_complement(oracle_mod):
+    """the "intended" junction semantics (src/alignment.h:542-544: entering J only AT the listed
+    target indices).  The reference cannot run it, but it is its own blacklist mode on the complement of the list --
+    which pins the port's whitelist restatement on the compiled reference."""
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = random.Random(8)
+    n_jump = 0
+    for k in range(120):
+        l2 = rng.randint(30, 220)
+        s2 = bytes(rng.choice(b"ACGT") for _ in range(l2))
+        a, b = sorted(rng.sample(range(5, l2 - 5), 2))
+        s1 = (s2[max(0, a - rng.randint(3, 25)):a] + s2[b:b + rng.randint(3, 25)]) or b"A"      # two "exons" around an "intron"
+        s1 = bytes(c if rng.random() > 0.05 else rng.choice(b"ACGT") for c in s1)
+        white = sorted(set([a, b - 1, b] + [rng.randrange(l2) for _ in range(rng.choice([0, 2, 5]))]))
+        black = [x for x in range(l2) if x not in white]
+        prm = dict(m=rng.randint(1, 4), u=rng.randint(-4, -1), o=rng.randint(-8, -2), e=rng.randint(-3, -1), j=rng.randint(-12, -2))
+        w = oracle_mod.port_align("fit", s1, s2, oracle_mod.Params(**prm, jump=2), white)
+        r = oracle_mod.ref_align("fit", s1, s2, oracle_mod.Params(**prm, jump=True), black)
+        assert (w.score, w.r1, w.r2) == (r.score, r.r1, r.r2), (k, prm, s1, s2, white)
+        n_jump += w.ops.count(b"N") > 0
+    assert n_jump > 20
