@@ -30,7 +30,7 @@ EXPORTS = ["at_default_params", "at_strerror", "at_version", "at_create", "at_de
            "at_device_count", "at_launch_count", "at_align_gla", "at_align_local_affine",
            "at_align_fit_affine_jump", "at_align_overlap", "at_edit_dist", "at_batch_create",
            "at_batch_run", "at_batch_sizes", "at_batch_fetch", "at_batch_free", "at_batch_align",
-           "at_pack_2bit", "at_cigar_to_string", "at_plan_slices"]
+           "at_pack_2bit", "at_cigar_to_string", "at_plan_slices", "at_host_alloc", "at_host_free"]
 
 
 class AtError(RuntimeError):
@@ -176,13 +176,16 @@ def pack_seqs(seqs):
     return np.ascontiguousarray(buf), off, lens
 
 
-def pack_2bit(buf, off, lens):
-    """byte batch (ACGT only) -> 2-bit batch with byte-aligned records (AT_SEQ_2BIT)."""
+def pack_2bit(buf, off, lens, align=1):
+    """byte batch (ACGT only) -> 2-bit batch (AT_SEQ_2BIT).  Records start on a multiple of `align` bytes: 1 = densest
+    (the format only asks for byte alignment); 16 lets the fill kernels read them with 128-bit loads."""
     lut = np.full(256, 255, np.uint8)
     for k, ch in enumerate(b"ACGT"):
         lut[ch] = k
     n = len(lens)
     nb = (lens.astype(np.uint64) + 3) // 4
+    nb_raw = nb
+    nb = (nb + np.uint64(align - 1)) // np.uint64(align) * np.uint64(align)
     poff = np.zeros(n, dtype=np.uint64)
     if n > 1:
         np.cumsum(nb[:-1], out=poff[1:])
@@ -199,7 +202,7 @@ def pack_2bit(buf, off, lens):
             codes = np.concatenate([codes, np.zeros((n, pad), np.uint8)], axis=1)
         c4 = codes.reshape(n, -1, 4)
         packed = (c4[:, :, 0] | (c4[:, :, 1] << 2) | (c4[:, :, 2] << 4) | (c4[:, :, 3] << 6)).astype(np.uint8)
-        out[:total] = packed.reshape(-1)
+        out[:total].reshape(n, int(nb[0]))[:, :int(nb_raw[0])] = packed
     else:
         for p in range(n):
             codes = lut[buf[int(off[p]):int(off[p]) + int(lens[p])]]

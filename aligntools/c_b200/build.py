@@ -57,6 +57,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return lib
 
 
+def build_variant(name: str, defines: list) -> str:
+    """A/B builds: the library compiled with extra -D flags into lib_<name>.so beside the product library (load it with
+    AT_LIB_PATH); used by tools/ab_*.sh to time kernel variants in one GPU call."""
+    out = os.path.join(HERE, f"lib_{name}.so")
+    objs = []
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(CSRC, s.replace(".cu", f".{name}.o"))
+        cmd = ["nvcc"] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(o)
+    for cmd, p in procs:
+        outp, _ = p.communicate()
+        if p.returncode:
+            sys.stderr.write(outp.decode())
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.run(["nvcc", "-arch=sm_100a", "-shared", "-o", out] + objs + ["-lpthread"], check=True)
+    return out
+
+
 def _build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB

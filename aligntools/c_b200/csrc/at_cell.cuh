@@ -127,6 +127,27 @@ template <typename T> AT_HD T opaque(T v)
 	return v;
 }
 
+// Which kernels spell the pointer algebra's adds as explicit multiply-adds (FMA pipe) instead of leaving the choice of
+// pipe to the compiler.  Measured (profiles/ab_fma_adds_r02.txt): the packed kernel is ALU-bound and gains 1.2 % (C2 fill
+// 31.11 -> 30.75 ms); the int32 kernels already lean on the FMA pipe and LOSE (C3 46.0 -> 54.2 ms, global 150 x 150
+// 1.35 -> 1.43 ms).  Hence: packed lanes only.
+#ifndef AT_CELL_FMA_ADDS
+#define AT_CELL_FMA_ADDS(PACKED) (PACKED)
+#endif
+
+// a * b + c as ONE multiply-add on the FMA pipe.  Written in PTX so that neither LLVM nor ptxas re-associates it into
+// IADD3 / LOP3 forms (ALU pipe); with b a register holding +-1 it is how these kernels add without touching the ALU pipe.
+AT_HD uint32_t fma_mad(uint32_t a, uint32_t b, uint32_t c)
+{
+#ifdef __CUDA_ARCH__
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+#else
+	return a * b + c;
+#endif
+}
+
 // values of the k_and / k_or kernel arguments (see CellConst::set)
 template <bool PACKED> AT_HD uint32_t cell_k_and() { return (uint32_t)~Lanes<PACKED>::rep(3); }
 template <bool PACKED> AT_HD uint32_t cell_k_or() { return (uint32_t)Lanes<PACKED>::rep(TAG_M); }
@@ -141,6 +162,7 @@ template <bool PACKED> struct CellConst {
 	T m_and, m_or; // Mk = (Mt & m_and) | m_or = clean | 2, as registers
 	T j_enter;     // 8 (jump - o) - 2, fused-add form: entering J from Mo' carries tag 1
 	T j_barred;    // the same on a black-listed target index: -inf
+	uint32_t one, neg1;   // +1 / -1 the compiler cannot see through (derived from k_or): multipliers of fma_mad
 	// k_and / k_or: ~3 and TAG_M in every lane half, handed in as KERNEL ARGUMENTS: constants the compiler can see
 	// become immediates, and a LOP3 takes only one -- (x & c1) | c2 would be two instructions on the binding pipe;
 	// with both in registers it is one
@@ -153,6 +175,8 @@ template <bool PACKED> struct CellConst {
 		o_m = V::delta(o) + V::rep(1);
 		m_and = (T)k_and;
 		m_or = (T)k_or;
+		one = (k_or >> 1) & 1u;      // TAG_M = 2 in the low half: always 1, but only at run time
+		neg1 = 0u - one;
 		j_enter = PACKED ? (T)0 : (T)(8 * (jp - o) - 2);
 		j_barred = PACKED ? (T)0 : (T)AT_NEG;
 	}
@@ -198,7 +222,7 @@ AT_HD typename Lanes<PACKED>::T cell_update(const CellConst<PACKED> &c, RowState
 	const T mk = opaque<T>((mt & c.m_and) | c.m_or);
 	const T lk = opaque<T>(lt & ~V::rep(4));
 	const T uk = opaque<T>(ut & ~V::rep(2));
-	const T mo = mk + c.o_m;
+	const T mo = AT_CELL_FMA_ADDS(PACKED) ? (T)fma_mad((uint32_t)mk, c.one, (uint32_t)c.o_m) : (T)(mk + c.o_m);
 	T h = V::vmax3(lk, mk, uk);
 	T jk = 0, jt = 0;
 	if (JUMP) {
@@ -207,7 +231,16 @@ AT_HD typename Lanes<PACKED>::T cell_update(const CellConst<PACKED> &c, RowState
 		h = V::vmax(h, jk);                              // J is the last argument of max5: it wins only when strictly greater
 	}
 	// pointer accumulator (FMA pipe): clean minus tagged, earliest step in the top nibble
-	st.x = st.x * mul + (((uint32_t)(lk + mk) - (uint32_t)(lt + mt)) + (uint32_t)uk * 4u - (uint32_t)ut * 4u);
+	if (AT_CELL_FMA_ADDS(PACKED)) {
+		uint32_t dx = fma_mad((uint32_t)mk, c.one, (uint32_t)lk);
+		dx = fma_mad((uint32_t)mt, c.neg1, dx);
+		dx = fma_mad((uint32_t)lt, c.neg1, dx);
+		dx = (uint32_t)uk * 4u + dx;
+		dx = (uint32_t)ut * 0xfffffffcu + dx;
+		st.x = st.x * mul + dx;
+	} else {
+		st.x = st.x * mul + (((uint32_t)(lk + mk) - (uint32_t)(lt + mt)) + (uint32_t)uk * 4u - (uint32_t)ut * 4u);
+	}
 	if (JUMP) st.xj = st.xj * mulj + ((uint32_t)jt - (uint32_t)jk);
 	const T d_next = st.h;
 	st.h = h; st.u = uk; st.mo = mo;

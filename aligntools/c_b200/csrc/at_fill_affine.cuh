@@ -69,6 +69,7 @@ struct FillArgs2 {
 	int             m, u, o, e, jp;
 	int             want_ptr;
 	uint32_t        k_and, k_or;   // cell_k_and / cell_k_or of the lane type (at_cell.cuh: constants that must stay in registers)
+	int             twobit;  // PROF: q / t hold 2-bit codes (AT_SEQ_2BIT, four symbols per byte, byte-aligned records; *_off are byte offsets)
 };
 
 template <int MODE, int R, bool JUMP, bool PACKED, bool PROF>
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 	const T ZERO = V::value(0);
 	const T NEGV = PACKED ? ZERO : (T)AT_NEG;                           // -inf stand-in (int32 lanes only)
 	const bool want_ptr = a.want_ptr != 0;
+	const bool twobit = PROF && a.twobit != 0;
 
 	for (;;) {
 		uint32_t job = 0;
@@ -125,6 +127,43 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 		// PROF: byte offset of the column's comb in the profile | blacklist bit
 		auto load_block = [&](uint32_t blk) {
 			const uint32_t base = blk * 256u;
+			if (PROF && twobit) {
+				// 2-bit targets resident in HBM: 256 columns = 64 bytes per pair.  Records that start on a 16-byte boundary are
+				// read with one 128-bit load per 64 columns (lanes 0-3: pair A, lanes 4-7: pair B) and handed round by shuffle;
+				// others with two byte loads per lane.  Lane k turns columns base + 8k .. + 7 into ring entries.
+				const uint8_t *pa = tA + (base >> 2), *pb = tB + (base >> 2);
+				uint32_t wa = 0, wb = 0;
+				if (base < l2) {
+					if ((((uintptr_t)tA | (uintptr_t)tB) & 15u) == 0) {
+						uint4 v = make_uint4(0, 0, 0, 0);
+						const uint32_t need = (min(l2 - base, 256u) + 63u) >> 6;             // 16-byte groups that hold columns of this block
+						if (lane < 8 && (uint32_t)(lane & 3) < need) v = __ldg((const uint4 *)((lane < 4 ? pa : pb) + 16 * (lane & 3)));
+						const int src = lane >> 3, comp = (lane >> 1) & 3, hi = (lane & 1) * 16;
+						const uint32_t xa0 = __shfl_sync(0xffffffffu, v.x, src), xa1 = __shfl_sync(0xffffffffu, v.y, src),
+						               xa2 = __shfl_sync(0xffffffffu, v.z, src), xa3 = __shfl_sync(0xffffffffu, v.w, src);
+						wa = ((comp == 0 ? xa0 : comp == 1 ? xa1 : comp == 2 ? xa2 : xa3) >> hi) & 0xffffu;
+						if (PACKED) {
+							const uint32_t xb0 = __shfl_sync(0xffffffffu, v.x, src + 4), xb1 = __shfl_sync(0xffffffffu, v.y, src + 4),
+							               xb2 = __shfl_sync(0xffffffffu, v.z, src + 4), xb3 = __shfl_sync(0xffffffffu, v.w, src + 4);
+							wb = ((comp == 0 ? xb0 : comp == 1 ? xb1 : comp == 2 ? xb2 : xb3) >> hi) & 0xffffu;
+						}
+					} else if (base + 8u * lane < l2) {
+						wa = (uint32_t)__ldg(pa + 2 * lane) | ((uint32_t)__ldg(pa + 2 * lane + 1) << 8);     // (one byte of slack behind the last record)
+						if (PACKED) wb = (uint32_t)__ldg(pb + 2 * lane) | ((uint32_t)__ldg(pb + 2 * lane + 1) << 8);
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const uint32_t idx = base + 8u * lane + k, slot = idx & (AT_RING - 1);
+					uint32_t v = (wa >> (2 * k)) & 3u;
+					if (PACKED) v = v * 4u + ((wb >> (2 * k)) & 3u);
+					v = idx < l2 ? v * COMB_BYTES : 0u;
+					if (JUMP && idx < l2) v |= __ldg(jm + idx) ? 1u : 0u;
+					ring16[slot] = (uint16_t)v;
+					if (slot < AT_RING_MIRROR) ring16[AT_RING + slot] = (uint16_t)v;
+				}
+				return;
+			}
 #pragma unroll
 			for (int k = 0; k < 8; ++k) {
 				const uint32_t idx = base + k * 32u + lane, slot = idx & (AT_RING - 1);
@@ -162,16 +201,19 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 		for (int r = 0; r < R; ++r) {
 			const uint32_t ri = row0 + r;
 			const int i = (int)ri + 1;
+			ac[r] = 0;
 			if (PACKED) {
-				const uint32_t ca = ri < l1A ? ((uint32_t)qA[ri] << SHIFT) : 0x0002u;
-				const uint32_t cb = ri < l1B ? ((uint32_t)qB[ri] << SHIFT) : 0x0002u;
-				ac[r] = ca | (cb << 16);
+				if (!PROF) {      // fallback variant: the read symbols, pre-shifted (the PROF variant reads them into its profile below)
+					const uint32_t ca = ri < l1A ? ((uint32_t)qA[ri] << SHIFT) : 0x0002u;
+					const uint32_t cb = ri < l1B ? ((uint32_t)qB[ri] << SHIFT) : 0x0002u;
+					ac[r] = ca | (cb << 16);
+				}
 				// running-max key offset on top of Mk = 8 M + 2: 5 - r for real rows (key = 8 M + 7 - r); -0x8000 sinks
 				// padded rows below every real key (per half, two's complement)
 				const uint32_t ka = ri < l1A ? (uint32_t)(5 - r) : 0x8000u, kb = ri < l1B ? (uint32_t)(5 - r) : 0x8000u;
 				crow[r] = (T)((ka & 0xffffu) | ((kb & 0xffffu) << 16));
 			} else {
-				ac[r] = ri < l1A ? ((uint32_t)qA[ri] << SHIFT) : 0x4u;
+				if (!PROF) ac[r] = ri < l1A ? ((uint32_t)qA[ri] << SHIFT) : 0x4u;
 				crow[r] = (T)(ri < l1A ? 5 - r : -(1 << 28));
 			}
 			// column 0 (left border), tags as cell_update leaves them: mo 3, u 1, h = the winner's
@@ -180,11 +222,13 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 			else                         { st[r].mo = NEGV | V::rep(3); st[r].u = NEGV | V::rep(1); st[r].h = NEGV | V::rep(TAG_M); }                  // :612-617
 			st[r].j = NEGV; st[r].x = 0; st[r].xj = 0;
 			if (PROF) {     // this lane's rows of the query profile: 8*s(read symbol, target symbol of code c)
-				const uint32_t qa = ri < l1A ? (uint32_t)qA[ri] : 0x100u, qb = (PACKED && ri < l1B) ? (uint32_t)qB[ri] : 0x100u;
+				uint32_t qa = 0x100u, qb = 0x100u;          // byte of the read symbol (2-bit reads: its code), 0x100 = no such row
+				if (ri < l1A) qa = twobit ? ((uint32_t)qA[ri >> 2] >> (2 * (ri & 3))) & 3u : (uint32_t)qA[ri];
+				if (PACKED && ri < l1B) qb = twobit ? ((uint32_t)qB[ri >> 2] >> (2 * (ri & 3))) & 3u : (uint32_t)qB[ri];
 				int sa[4], sb[4];
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
-					const uint32_t sy = (a.syms >> (8 * c)) & 255u;
+					const uint32_t sy = twobit ? (uint32_t)c : (a.syms >> (8 * c)) & 255u;
 					sa[c] = 8 * (qa == sy ? m : u); sb[c] = 8 * (qb == sy ? m : u);
 				}
 #pragma unroll

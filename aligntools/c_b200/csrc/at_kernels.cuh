@@ -74,6 +74,7 @@ struct TraceArgs {
 	uint8_t        *aln1, *aln2;          // dense columns of the chunk
 	int             mode, jump;
 	int             lookahead;             // few, long walks (latency-bound): prefetch the pointer sectors ahead of the walker
+	int             twobit;                // q / t hold 2-bit codes (four symbols per byte, A C G T = 0..3; byte-aligned records)
 };
 
 // Cursor over a pair's pointer block (layout: at_kernels.cuh header).  The word of cell (i, j) is
@@ -235,8 +236,10 @@ __global__ void __launch_bounds__(128) at_traceback_emit(const TraceArgs a)
 			const uint32_t op = src[n - 1 - x], len = op >> 4, code = op & 15u;
 			const bool gap1 = code == CIG_D || code == CIG_N, gap2 = code == CIG_I;
 			for (uint32_t c = lane; c < len; c += 32) {
-				a1[col + c] = gap1 ? (uint8_t)'-' : q[i + c];
-				a2[col + c] = gap2 ? (uint8_t)'-' : tg[j + c];
+				uint8_t x = (uint8_t)'-', y = (uint8_t)'-';
+				if (!gap1) { const uint32_t k = i + c; x = a.twobit ? (uint8_t)"ACGT"[(q[k >> 2] >> (2 * (k & 3))) & 3] : q[k]; }
+				if (!gap2) { const uint32_t k = j + c; y = a.twobit ? (uint8_t)"ACGT"[(tg[k >> 2] >> (2 * (k & 3))) & 3] : tg[k]; }
+				a1[col + c] = x; a2[col + c] = y;
 			}
 			col += len; if (!gap1) i += len; if (!gap2) j += len;
 		}

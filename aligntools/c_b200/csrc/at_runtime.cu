@@ -189,6 +189,7 @@ struct Chunk {
 // Sub-slices of one device take turns (in pair order) on the host->device copy of their sequences.
 struct UploadGate {
 	std::mutex mu; std::condition_variable cv; uint64_t turn = 0;
+	cudaEvent_t last = nullptr;      // recorded behind the previous turn's copies: the next turn's stream waits for it, not the host
 	void wait_for(uint64_t k) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return turn >= k; }); }
 	void pass(uint64_t k) { std::lock_guard<std::mutex> lk(mu); if (turn < k + 1) { turn = k + 1; cv.notify_all(); } }    // idempotent
 };
@@ -208,6 +209,7 @@ struct Shard {
 	DevBuf<uint8_t> d_symmap; DevBuf<uint32_t> d_symset;
 	bool prof = false; uint32_t syms = 0;      // query-profile variant of K1: the targets use <= 4 distinct bytes
 	bool bits = false;                         // bit-parallel edit distance: `-u 1` and reads of <= 8 distinct bytes
+	bool twobit = false;                       // the sequences stay 2-bit packed in HBM (AT_SEQ_2BIT input consumed directly by K1 / K3)
 	BufCache cache;                            // released device blocks, reused by this shard's next allocations
 	struct UploadGate *gate = nullptr; uint64_t gate_turn = 0;   // pipelined path: sub-slices upload their sequences one at a time, in pair order
 	bool workspace = false;                    // pipeline workspace: reused for many sub-slices, buffers get head-room
@@ -216,6 +218,7 @@ struct Shard {
 	uint64_t cells = 0, ptr_bytes = 0, t_span = 0;   // t_span: bytes of d_t that hold the caller's target span
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t evk[2] = {nullptr, nullptr};
+	cudaEvent_t ev_up = nullptr;               // behind this shard's sequence upload (pipelined path: orders the sub-slices' copies)
 	// last-run timing
 	double fill_ms = 0, tb_ms = 0, dev_ms = 0, domk_ms = 0; uint64_t domk_cells = 0, launches = 0; uint32_t domk_kind = 0, domk_r = 0, domk_flags = 0;
 	int rc = AT_OK;
@@ -258,9 +261,11 @@ __global__ void at_unpack_2bit(const uint8_t *src, const uint64_t *src_off, cons
 }
 
 // upload one side (reads or targets) of a shard; rewrites offsets relative to the device buffer
+// `resident` (2-bit input only): the packed records stay as they are -- d_bytes receives them, d_off their byte
+// offsets -- and the kernels read the codes directly; otherwise 2-bit input is expanded to bytes on the device.
 static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t *src, const uint64_t *off,
                        const uint32_t *len, DevBuf<uint8_t> &d_bytes, DevBuf<uint8_t> &d_packed, DevBuf<uint64_t> &d_off,
-                       DevBuf<uint32_t> &d_len, uint64_t *span_bytes)
+                       DevBuf<uint32_t> &d_len, uint64_t *span_bytes, bool resident)
 {
 	const uint32_t n = s.n;
 	cudaStream_t st = s.stream;
@@ -274,7 +279,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 		lo = std::min(lo, o); hi = std::max(hi, o + nbytes);
 		unp[k] = tot; tot += len[s.p0 + k];
 	}
-	DevBuf<uint8_t> &raw = encoding == AT_SEQ_2BIT ? d_packed : d_bytes;
+	DevBuf<uint8_t> &raw = (encoding == AT_SEQ_2BIT && !resident) ? d_packed : d_bytes;
 	if (monotonic && hi - lo <= 2 * tot + 64) {          // one bulk copy of the caller's span
 		CU(h, raw.alloc(hi - lo + AT_SEQ_SLACK));
 		CU(h, cudaMemcpyAsync(raw.p, src + lo, hi - lo, cudaMemcpyHostToDevice, st));
@@ -289,13 +294,12 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 			memcpy(stage.data() + pos, src + off[s.p0 + k], nbytes); pos += nbytes;
 		}
 		CU(h, raw.alloc(pos + AT_SEQ_SLACK));
-		CU(h, cudaMemcpyAsync(raw.p, stage.data(), pos, cudaMemcpyHostToDevice, st));
-		CU(h, cudaStreamSynchronize(st));
+		CU(h, cudaMemcpyAsync(raw.p, stage.data(), pos, cudaMemcpyHostToDevice, st));      // pageable source: staged before the call returns
 		*span_bytes = pos;
 	}
 	CU(h, d_off.alloc(n)); CU(h, d_len.alloc(n));
 	CU(h, cudaMemcpyAsync(d_len.p, len + s.p0, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-	if (encoding == AT_SEQ_2BIT) {
+	if (encoding == AT_SEQ_2BIT && !resident) {
 		DevBuf<uint64_t> d_src_off;
 		CU(h, d_src_off.alloc(n));
 		CU(h, cudaMemcpyAsync(d_src_off.p, rel.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -304,13 +308,14 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 		at_unpack_2bit<<<n, 128, 0, st>>>(d_packed.p, d_src_off.p, d_off.p, d_len.p, n, d_bytes.p);
 		CU(h, cudaGetLastError());
 		h->launches++;
-		CU(h, cudaStreamSynchronize(st));
-		d_src_off.release();
+		d_src_off.release();      // stream-ordered: reused only by later work of this stream
 		*span_bytes = tot;
 	} else {
 		CU(h, cudaMemcpyAsync(d_off.p, rel.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-		CU(h, cudaStreamSynchronize(st));
 	}
+	// No synchronisation here: `rel` / `unp` / `stage` are pageable, so the runtime has staged them by the time
+	// cudaMemcpyAsync returns; the caller's (possibly pinned) sequence buffers stay valid until setup_shard's one
+	// synchronisation at its end.
 	return AT_OK;
 }
 
@@ -339,6 +344,7 @@ static void free_shard(Shard &s)
 	release_chunks(s);
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
 	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
+	if (s.ev_up) cudaEventDestroy(s.ev_up);
 	s.cache.flush(s.stream);
 	tl_cache = nullptr; tl_big = nullptr;
 }
@@ -367,8 +373,7 @@ static int scan_alphabet(at_handle *h, Shard &s, const uint8_t *d_bytes, uint64_
 static int upload_symmap(at_handle *h, Shard &s, const uint8_t map[256])
 {
 	CU(h, s.d_symmap.alloc(256));
-	CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, s.stream));
-	CU(h, cudaStreamSynchronize(s.stream));
+	CU(h, cudaMemcpyAsync(s.d_symmap.p, map, 256, cudaMemcpyHostToDevice, s.stream));      // `map` is pageable stack memory: staged before the call returns
 	return AT_OK;
 }
 
@@ -433,7 +438,6 @@ static int build_jump_mask(at_batch *b, Shard &s, const at_batch_input *in)
 	at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, s.d_t_off.p, s.d_t_len.p, n, s.d_jmask.p, whitelist ? 0 : 1);
 	CU(h, cudaGetLastError());
 	h->launches++;
-	CU(h, cudaStreamSynchronize(st));
 	return AT_OK;
 }
 
@@ -460,10 +464,25 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	{
 		// a pipeline worker waits for the uploads of the sub-slices before its own: the first (small) sub-slice's
 		// sequences are not held up behind a later, larger one sharing the copy engine, and its fill starts early
-		if (s.gate) s.gate->wait_for(s.gate_turn);
-		rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span);
-		if (!rc) rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span);
-		if (s.gate) s.gate->pass(s.gate_turn);
+		// 2-bit input stays packed in HBM when every pair of the shard runs on K1's query-profile variant (affine mode
+		// without jump state, reads of at most 256 rows): the fill reads the codes with 128-bit / byte loads and the
+		// traceback decodes them; no expansion kernel, a quarter of the sequence bytes.  Anything else expands to bytes.
+		s.twobit = false;
+		if (in->encoding == AT_SEQ_2BIT && b->mode <= AT_FIT && !(b->mode == AT_FIT && b->prm.jump) && !getenv("AT_NO_PROFILE") && !getenv("AT_NO_2BIT_RESIDENT")) {
+			s.twobit = true;
+			for (uint32_t k = 0; k < n && s.twobit; ++k) s.twobit = in->q_len[s.p0 + k] <= 32u * MAXR;
+		}
+		if (s.gate) {
+			s.gate->wait_for(s.gate_turn);
+			if (s.gate->last) CU(h, cudaStreamWaitEvent(st, s.gate->last, 0));      // copy engine: earlier sub-slices first
+		}
+		rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span, s.twobit);
+		if (!rc) rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span, s.twobit);
+		if (s.gate) {
+			if (!s.ev_up) CU(h, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
+			if (!rc) { CU(h, cudaEventRecord(s.ev_up, st)); s.gate->last = s.ev_up; }
+			s.gate->pass(s.gate_turn);
+		}
 		if (rc) return rc;
 	}
 	s.d_q2.release(); s.d_t2.release();
@@ -663,7 +682,6 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 			CU(h, c.d_scratch_off.alloc(nc));
 			CU(h, cudaMemcpyAsync(c.d_scratch_off.p, c.h_scratch_off.data(), nc * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 		}
-		CU(h, cudaStreamSynchronize(st));
 	}
 	mark("plan+jobs");
 	if (max_bnd_elems && s.d_bnd.alloc(max_bnd_elems * (linear ? sizeof(uint64_t) : sizeof(int4)) + 64) != cudaSuccess) { set_err(h, "stripe boundary slabs of %llu MB", (unsigned long long)((max_bnd_elems * (linear ? 8 : 16)) >> 20)); return AT_E_NOMEM; }
@@ -677,7 +695,6 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	if (max_scratch_words && s.d_scratch.alloc(max_scratch_words) != cudaSuccess) { set_err(h, "traceback scratch of %llu MB", (unsigned long long)(max_scratch_words >> 18)); return AT_E_NOMEM; }
 	CU(h, s.d_rclass.alloc(n));
 	CU(h, cudaMemcpyAsync(s.d_rclass.p, s.h_rclass.data(), n, cudaMemcpyHostToDevice, st));
-	CU(h, cudaStreamSynchronize(st));
 	if (max_chunk_words) {
 		cudaError_t e = s.d_ptr.alloc(max_chunk_words + (s.workspace && max_chunk_words > s.d_ptr.n ? max_chunk_words / 16 : 0));
 		if (e != cudaSuccess) { set_err(h, "pointer arena of %llu MB: %s", (unsigned long long)(max_chunk_words >> 18), cudaGetErrorString(e)); return AT_E_NOMEM; }
@@ -685,6 +702,10 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	for (auto &e : s.ev) if (!e) CU(h, cudaEventCreate(&e));
 	for (auto &e : s.evk) if (!e) CU(h, cudaEventCreate(&e));
 	mark("arena");
+	// the ONE synchronisation of the set-up: every upload has left the caller's buffers (they may be reused or freed once
+	// at_batch_create / the sub-slice's set-up returns) and the shard's own host vectors
+	CU(h, cudaStreamSynchronize(st));
+	mark("sync");
 	if (trace_setup) fprintf(stderr, "[at setup] pairs %u:%s\n", n, tl.c_str());
 	return AT_OK;
 }
@@ -957,7 +978,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				fa.counter = s.d_counter.p + (l.kind == LK_PACKED ? 16 : 0) + l.r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
 				fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
 				fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
-				fa.want_ptr = b->traceback ? 1 : 0;
+				fa.want_ptr = b->traceback ? 1 : 0; fa.twobit = s.twobit ? 1 : 0;
 				fa.k_and = l.kind == LK_PACKED ? cell_k_and<true>() : cell_k_and<false>(); fa.k_or = l.kind == LK_PACKED ? cell_k_or<true>() : cell_k_or<false>();
 				void *kargs[] = {(void *)&fa};
 				CU(h, cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warps), kargs, dyn_smem, st));
@@ -983,7 +1004,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			ta.ops_off = c.d_ops_off.p; ta.cols_off = c.d_cols_off.p;
 			ta.scratch = s.d_scratch.p; ta.scratch_off = c.d_scratch_off.p;
 			ta.cigar = nullptr; ta.aln1 = nullptr; ta.aln2 = nullptr;
-			ta.mode = b->mode; ta.jump = jump ? 1 : 0;
+			ta.mode = b->mode; ta.jump = jump ? 1 : 0; ta.twobit = s.twobit ? 1 : 0;
 			// few long walks: one walker per warp, prefetching ahead; with many walks, or short ones (a few hundred
 			// steps: nothing to prefetch far ahead of), the chase is throughput-bound and the prefetches only add traffic
 			ta.lookahead = nc < 32768u && c.scratch_words / nc >= 2048 ? 1 : 0;
@@ -1057,7 +1078,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 		if ((int)ci == dom_chunk) {
 			CU(h, cudaEventElapsedTime(&ms, s.evk[0], s.evk[1])); s.domk_ms = ms; s.domk_cells = dom_cells;
 			const Launch &dl = c.launches[dom_launch];
-			s.domk_kind = (uint32_t)dl.kind; s.domk_r = (uint32_t)dl.r; s.domk_flags = (s.prof ? 1u : 0u) | (jump ? 2u : 0u);
+			s.domk_kind = (uint32_t)dl.kind; s.domk_r = (uint32_t)dl.r; s.domk_flags = (s.prof ? 1u : 0u) | (jump ? 2u : 0u) | (s.twobit ? 4u : 0u);
 		}
 		if (ci + 1 == s.chunks.size()) { CU(h, cudaEventElapsedTime(&ms, e_first, e_tb)); s.dev_ms = ms; }
 	}
@@ -1162,6 +1183,15 @@ extern "C" int at_batch_fetch(at_batch *b, at_batch_output *out)
 }
 
 #include "at_pipeline.inl"      // at_batch_align: the pipelined one-shot path (same translation unit)
+
+extern "C" void *at_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+extern "C" void at_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int64_t at_pack_2bit(const char *seq, uint64_t n, uint8_t *dst)
 {

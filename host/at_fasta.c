@@ -12,6 +12,9 @@
  *   '+'      : FASTQ -- the rest of that line is skipped and quality lines are consumed until they
  *              cover the sequence length; a quality string of a different length (or a missing one)
  *              ends the input without yielding the record (kseq returns -2, the caller's loop stops)
+ *
+ * The input is STREAMED: the (possibly gzip'ed) file is inflated through a 256 KiB window, so a batch of any
+ * size is parsed in constant memory while earlier blocks are already on the GPU (host/alignTools.c, `batch`).
  */
 #include "at_fasta.h"
 
@@ -20,11 +23,17 @@
 #include <string.h>
 #include <zlib.h>
 
+#ifndef AT_FASTA_WINDOW
+#define AT_FASTA_WINDOW (1u << 18)      /* the tests also build the reader with a window of a few bytes */
+#endif
+
 typedef struct { char *s; size_t l, m; } strbuf;
 
 struct at_fasta {
-	unsigned char *buf;     /* the whole inflated file */
-	size_t n, pos;
+	gzFile fp;
+	unsigned char *buf;     /* the window of inflated bytes */
+	size_t n, pos;          /* valid bytes / read position in the window */
+	int eof;                /* the stream is exhausted (or unreadable: whatever was inflated so far is the input) */
 	int header_seen;        /* the next record's '>' / '@' has already been consumed */
 	int have_comment;       /* comment.s holds a string (possibly a previous record's) */
 	strbuf name, comment, seq;
@@ -41,14 +50,6 @@ static int sb_reserve(strbuf *b, size_t need)
 	return 0;
 }
 
-static int sb_set(strbuf *b, const unsigned char *src, size_t len)
-{
-	if (sb_reserve(b, len + 1)) return -1;
-	memcpy(b->s, src, len);
-	b->l = len; b->s[len] = 0;
-	return 0;
-}
-
 static int sb_append(strbuf *b, const unsigned char *src, size_t len)
 {
 	if (sb_reserve(b, b->l + len + 1)) return -1;
@@ -57,85 +58,97 @@ static int sb_append(strbuf *b, const unsigned char *src, size_t len)
 	return 0;
 }
 
+static int sb_clear(strbuf *b)
+{
+	if (sb_reserve(b, 1)) return -1;
+	b->l = 0; b->s[0] = 0;
+	return 0;
+}
+
+/* make sure the window holds an unread byte; 0 at the end of the input */
+static int more(at_fasta *f)
+{
+	if (f->pos < f->n) return 1;
+	if (f->eof) return 0;
+	const int got = gzread(f->fp, f->buf, AT_FASTA_WINDOW);
+	if (got <= 0) { f->eof = 1; f->n = f->pos = 0; return 0; }
+	f->n = (size_t)got; f->pos = 0;
+	return 1;
+}
+
 at_fasta *at_fasta_open(const char *path)
 {
 	gzFile fp = path ? gzopen(path, "r") : NULL;
 	if (!fp) return NULL;
 	at_fasta *f = (at_fasta *)calloc(1, sizeof *f);
-	if (!f) { gzclose(fp); return NULL; }
-	size_t cap = 1 << 16;
-	f->buf = (unsigned char *)malloc(cap);
-	while (f->buf) {
-		if (f->n == cap) {
-			cap *= 2;
-			unsigned char *p = (unsigned char *)realloc(f->buf, cap);
-			if (!p) { free(f->buf); f->buf = NULL; break; }
-			f->buf = p;
-		}
-		const size_t want = cap - f->n;
-		int got = gzread(fp, f->buf + f->n, (unsigned)(want > (1u << 30) ? (1u << 30) : want));
-		if (got <= 0) break;      /* end of file, or an unreadable stream: whatever was inflated so far is the input */
-		f->n += (size_t)got;
-	}
-	gzclose(fp);
-	if (!f->buf) { free(f); return NULL; }
+	if (f) f->buf = (unsigned char *)malloc(AT_FASTA_WINDOW);
+	if (!f || !f->buf) { free(f); gzclose(fp); return NULL; }
+	gzbuffer(fp, 1u << 17);
+	f->fp = fp;
 	return f;
 }
 
 void at_fasta_close(at_fasta *f)
 {
 	if (!f) return;
+	if (f->fp) gzclose(f->fp);
 	free(f->buf); free(f->name.s); free(f->comment.s); free(f->seq.s);
 	free(f);
 }
 
-/* end of the line that starts at `from`: index of its '\n', or n */
-static size_t line_end(const at_fasta *f, size_t from)
-{
-	const unsigned char *p = from < f->n ? (const unsigned char *)memchr(f->buf + from, '\n', f->n - from) : NULL;
-	return p ? (size_t)(p - f->buf) : f->n;
-}
-
-/* append the rest of the current line to b; CR rule of the line reader.  Returns 0 when the
- * input was already exhausted (nothing appended, no CR rule), 1 otherwise. */
+/* append the rest of the current line to b (b == NULL: skip it) and consume its '\n'; CR rule of the line reader.
+ * Returns 0 when the input was already exhausted (nothing appended, no CR rule), 1 when the line ended with
+ * '\n', 2 when it ended with the input. */
 static int take_line(at_fasta *f, strbuf *b)
 {
-	if (f->pos >= f->n) return 0;
-	const size_t e = line_end(f, f->pos);
-	sb_append(b, f->buf + f->pos, e - f->pos);
-	f->pos = e < f->n ? e + 1 : f->n;
-	if (b->l > 1 && b->s[b->l - 1] == '\r') b->s[--b->l] = 0;
-	return 1;
+	if (!more(f)) return 0;
+	int ended = 2;
+	while (more(f)) {
+		const unsigned char *p = f->buf + f->pos;
+		const unsigned char *nl = (const unsigned char *)memchr(p, '\n', f->n - f->pos);
+		const size_t len = nl ? (size_t)(nl - p) : f->n - f->pos;
+		if (b) sb_append(b, p, len);
+		f->pos += len;
+		if (nl) { ++f->pos; ended = 1; break; }
+	}
+	if (b && b->l > 1 && b->s[b->l - 1] == '\r') b->s[--b->l] = 0;
+	return ended;
 }
 
 int at_fasta_next(at_fasta *f, at_fasta_rec *rec)
 {
 	if (!f || !rec) return 0;
 	if (!f->header_seen) {
-		while (f->pos < f->n && f->buf[f->pos] != '>' && f->buf[f->pos] != '@') ++f->pos;
-		if (f->pos >= f->n) return 0;
-		++f->pos;
+		for (;;) {
+			if (!more(f)) return 0;
+			const unsigned char c = f->buf[f->pos++];
+			if (c == '>' || c == '@') break;
+		}
 	}
 	f->header_seen = 0;
-	if (f->pos >= f->n) return 0;                 /* a lone header character at the very end */
-	/* name */
-	size_t k = f->pos;
-	while (k < f->n && !isspace(f->buf[k])) ++k;
-	if (sb_set(&f->name, f->buf + f->pos, k - f->pos)) return 0;
-	const int delim = k < f->n ? f->buf[k] : 0;
-	f->pos = k < f->n ? k + 1 : f->n;
+	if (!more(f)) return 0;                       /* a lone header character at the very end */
+	/* name: up to the first isspace() byte */
+	if (sb_clear(&f->name)) return 0;
+	int delim = 0;
+	while (more(f)) {
+		size_t k = f->pos;
+		while (k < f->n && !isspace(f->buf[k])) ++k;
+		if (sb_append(&f->name, f->buf + f->pos, k - f->pos)) return 0;
+		f->pos = k;
+		if (k < f->n) { delim = f->buf[f->pos++]; break; }
+	}
 	/* comment */
-	if (delim != '\n' && f->pos < f->n) {
-		f->comment.l = 0;
-		if (f->comment.s) f->comment.s[0] = 0;
+	int own_comment = 0;
+	if (delim != '\n' && more(f)) {
+		if (sb_clear(&f->comment)) return 0;
 		take_line(f, &f->comment);
-		if (!f->comment.s) sb_set(&f->comment, (const unsigned char *)"", 0);
 		f->have_comment = 1;
+		own_comment = 1;
 	}
 	/* sequence */
-	if (sb_set(&f->seq, (const unsigned char *)"", 0)) return 0;
+	if (sb_clear(&f->seq)) return 0;
 	int c = -1;
-	while (f->pos < f->n) {
+	while (more(f)) {
 		c = f->buf[f->pos++];
 		if (c == '>' || c == '+' || c == '@') break;
 		if (c != '\n') {
@@ -147,9 +160,7 @@ int at_fasta_next(at_fasta *f, at_fasta_rec *rec)
 	}
 	if (c == '>' || c == '@') f->header_seen = 1;
 	if (c == '+') {                               /* FASTQ: skip the '+' line, then the quality string */
-		const size_t e = line_end(f, f->pos);
-		if (e >= f->n) return 0;                  /* no quality string */
-		f->pos = e + 1;
+		if (take_line(f, NULL) != 1) return 0;    /* no quality string */
 		strbuf qual = {0, 0, 0};
 		while (take_line(f, &qual) && qual.l < f->seq.l) {}
 		const size_t ql = qual.l;
@@ -158,6 +169,7 @@ int at_fasta_next(at_fasta *f, at_fasta_rec *rec)
 	}
 	rec->name = f->name.s;
 	rec->comment = f->have_comment ? f->comment.s : NULL;
+	rec->own_comment = own_comment;
 	rec->seq = f->seq.s;
 	rec->seq_len = strlen(f->seq.s);              /* the reference strdup()s: an embedded NUL ends the sequence */
 	return 1;

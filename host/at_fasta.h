@@ -4,8 +4,8 @@
  * src/alignment.h:23; kseq_read src/kseq.h:189-229) inside kstring_read (src/alignment.h:217-262).
  * This is an independent reader with the same observable record semantics (what counts as a
  * header, name / comment split, multi-line sequences, FASTQ quality skipping, CR stripping,
- * the comment carried over from the previous record when a header has none), written as an
- * in-memory scanner over the fully inflated file instead of a 16 KiB stream buffer.
+ * the comment carried over from the previous record when a header has none), streaming the
+ * inflated bytes through a 256 KiB window.
  */
 #ifndef AT_FASTA_H
 #define AT_FASTA_H
@@ -19,6 +19,7 @@ extern "C" {
 typedef struct at_fasta_rec {
 	const char *name;      /* NUL-terminated, owned by the reader, valid until the next call */
 	const char *comment;   /* NULL when no header so far carried a comment (see at_fasta_next) */
+	int         own_comment; /* 1 when THIS record's header carried the comment (0: inherited from an earlier record, the kseq quirk) */
 	const char *seq;       /* NUL-terminated; seq_len == strlen(seq) as the reference strdup()s it */
 	size_t      seq_len;
 } at_fasta_rec;

@@ -202,6 +202,12 @@ int  at_batch_align(at_handle *h, int mode, const at_params *p, const at_batch_i
  * rank's slice.  Pure host code. */
 int  at_plan_slices(const uint32_t *q_len, const uint32_t *t_len, uint64_t n_pairs, uint32_t parts, uint64_t *cut);
 
+/* Page-locked host memory for the caller's batch buffers: with pinned inputs and outputs the copies of at_batch_align
+ * overlap its kernels (pageable memory works too, through the driver's staging buffers).  NULL when the allocation
+ * fails.  Pure convenience over cudaHostAlloc / cudaFreeHost, so that a C host needs no CUDA headers. */
+void *at_host_alloc(size_t bytes);
+void  at_host_free(void *p);
+
 /* Helpers: 2-bit packing (returns number of bytes written = (n+3)/4, or <0 when a symbol
  * is not one of ACGT/acgt... only upper-case ACGT are accepted: the reference compares
  * bytes verbatim, so folding case would change results) and CIGAR rendering. */

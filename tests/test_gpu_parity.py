@@ -161,6 +161,31 @@ def test_config2_2bit_encoding(A, aligner, oracle_mod):
                         w["t"], w["t_off"], w["t_len"], encoding=1, q_dev=q2, qo_dev=qo2, t_dev=t2, to_dev=to2)
 
 
+@pytest.mark.parametrize("mode", ["local", "global", "fit"])
+@pytest.mark.parametrize("align", [1, 16])
+def test_2bit_resident_sequences(A, aligner, oracle_mod, mode, align):
+    """AT_SEQ_2BIT input whose pairs all run on K1 stays 2-bit packed in HBM: the fill reads the codes directly (128-bit
+    loads when the records start on 16-byte boundaries, byte loads otherwise) and the traceback decodes them for r1 / r2.
+    Ragged lengths, packed s16x2 and int32 lanes, score + end cell + alignment strings + CIGAR against the oracle."""
+    rng = random.Random(100 + align + len(mode))
+    q, t = [], []
+    for k in range(400):
+        l2 = 200 if k < 250 else rng.randint(2, 700)                # equal l2 -> packed jobs in local mode
+        l1 = rng.randint(1, min(l2, 256))
+        s2 = bytes(rng.choice(b"ACGT") for _ in range(l2))
+        st = rng.randrange(0, l2 - l1 + 1)
+        s1 = bytes(c if rng.random() > 0.08 else rng.choice(b"ACGT") for c in s2[st:st + l1])
+        q.append(s1); t.append(s2)
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    q2, qo2, _ = A.pack_2bit(qb, qo[:-1].copy(), ql, align=align)
+    t2, to2, _ = A.pack_2bit(tb, to[:-1].copy(), tl, align=align)
+    prm = dict(m=2, u=-3, o=-4, e=-1, j=-7, jump=False)
+    tm = check_batch_vs_port(A, aligner, oracle_mod, mode, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl,
+                             encoding=1, q_dev=q2, qo_dev=qo2, t_dev=t2, to_dev=to2)
+    assert tm.fill_kernel_flags & 4, "the batch should have stayed 2-bit resident"
+
+
 def test_config3_shape_fit_jump(A, aligner, oracle_mod):
     """BASELINE config 3 shape: fit -s -j -10, 2 kbp transcripts vs 20 kbp two-gene targets."""
     from aligntools.c_b200 import synth

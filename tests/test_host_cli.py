@@ -65,6 +65,25 @@ def test_fasta_reader_matches_kseq_fixtures(built, tmp_path):
         assert got == base64.b64decode(c["dump_b64"]), c["name"]
 
 
+def test_fasta_reader_streams_across_window_boundaries(built, tmp_path):
+    """The reader inflates its input through a fixed window; rebuilt with windows of 1, 3 and 7 bytes every token of
+    every fixture straddles a refill, and the records must still come out as kseq's."""
+    with open(os.path.join(GOLD, "fasta_cases.json")) as f:
+        cases = json.load(f)["cases"]
+    host = os.path.join(ROOT, "host")
+    for win in (1, 3, 7):
+        exe = tmp_path / f"dump_w{win}"
+        subprocess.run(["gcc", "-std=gnu11", "-O1", f"-DAT_FASTA_WINDOW={win}u", "-I", host, os.path.join(host, "at_fasta_dump.c"),
+                        os.path.join(host, "at_fasta.c"), "-o", str(exe), "-lz"], check=True)
+        for c in cases:
+            p = tmp_path / (c["name"] + f"_w{win}" + (".gz" if c["gz"] else ".fa"))
+            data = base64.b64decode(c["input_b64"])
+            with (gzip.open(p, "wb") if c["gz"] else open(p, "wb")) as f:
+                f.write(data)
+            got = subprocess.run([str(exe), str(p)], capture_output=True).stdout
+            assert got == base64.b64decode(c["dump_b64"]), (win, c["name"])
+
+
 def test_fasta_reader_matches_live_reference(built, oracle_mod, tmp_path):
     """Random record soups through both parsers (only where oracle/_ref was built)."""
     if not oracle_mod.have_ref():
@@ -220,3 +239,99 @@ def test_cli_beside_the_compiled_reference(built, oracle_mod, tmp_path):
             assert ours.returncode == ref.returncode, (cmd, fn, ours.stderr[-200:])
             assert ours.stdout == ref.stdout, (cmd, fn)
             assert ours.stderr == ref.stderr.replace(oracle_mod.REF_CLI.encode(), CLI.encode()), (cmd, fn)
+
+
+def _random_pairs(rng, n, jump_sites=True):
+    pairs = []
+    for k in range(n):
+        l1 = rng.randint(5, 300)
+        s1 = "".join(rng.choice("ACGT") for _ in range(l1))
+        s2 = "".join(rng.choice("ACGT") for _ in range(rng.randint(0, 30))) + \
+            "".join(c if rng.random() > 0.08 else rng.choice("ACGT") for c in s1) + \
+            "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 200)))
+        com = "|".join(str(rng.randrange(len(s2))) for _ in range(rng.randint(1, 5))) if jump_sites else None
+        pairs.append((s1, s2, com))
+    return pairs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,opts", [("local", ["-m", "2", "-u", "-2", "-o", "-5", "-e", "-2"]), ("fit", ["-s", "-j", "-6"]), ("edit", ["-u", "1"])])
+def test_batch_streams_blocks(built, tmp_path, mode, opts):
+    """The batch sub-command streams its input in blocks (-B pairs per block: parse block k+1 while block k is on
+    the GPU, print block k-1): the output must not depend on the block size, also for gzip'ed input."""
+    import random
+    pairs = _random_pairs(random.Random(4), 157)
+    fa = tmp_path / "pairs.fa"
+    _write_pairs(fa, pairs)
+    gz = tmp_path / "pairs.fa.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(fa.read_bytes())
+    whole = subprocess.run([CLI, "batch", mode] + opts + [str(fa)], capture_output=True)
+    assert whole.returncode == 0, whole.stderr[-300:]
+    for blk, src in (("1", fa), ("7", gz), ("64", fa), ("157", fa)):
+        for fmt in ([], ["-c"], ["-S"]):
+            ref = whole.stdout if not fmt else subprocess.run([CLI, "batch", mode] + opts + fmt + [str(fa)], capture_output=True).stdout
+            pr = subprocess.run([CLI, "batch", mode] + opts + fmt + ["-B", blk, str(src)], capture_output=True)
+            assert pr.returncode == 0, pr.stderr[-300:]
+            assert pr.stdout.replace(str(src).encode(), b"F").replace(b" -B " + blk.encode(), b"") == ref.replace(str(fa).encode(), b"F"), (blk, fmt)
+
+
+@pytest.mark.gpu
+def test_batch_sam_records(built, oracle_mod, tmp_path):
+    """-S: SAM-like records.  Every record is checked against the oracle: POS is the first aligned target base, the
+    CIGAR (with S for the read's unaligned ends) consumes exactly the read, and replaying it gives the oracle's
+    alignment columns; AS is the score.  The header carries the @PG line the reference builds (src/main.c:36-38)."""
+    import random
+    pairs = _random_pairs(random.Random(12), 60, jump_sites=False)
+    fa = tmp_path / "pairs.fa"
+    _write_pairs(fa, pairs)
+    import re
+    for mode, prm in (("local", oracle_mod.Params(2, -2, -5, -2, -10, False)), ("global", oracle_mod.Params()), ("overlap", oracle_mod.Params())):
+        opts = ["-m", "2", "-u", "-2", "-o", "-5", "-e", "-2"] if mode == "local" else []
+        pr = subprocess.run([CLI, "batch", mode] + opts + ["-S", str(fa)], capture_output=True)
+        assert pr.returncode == 0, pr.stderr[-300:]
+        lines = pr.stdout.decode().strip().split("\n")
+        assert lines[0] == "@HD\tVN:1.6\tSO:unsorted" and lines[1].startswith("@PG\tID:alignTools\tPN:alignTools\tVN:0.7.23-r15\tCL:")
+        recs = [ln.split("\t") for ln in lines[2:]]
+        assert len(recs) == len(pairs)
+        for k, (f, (s1, s2, _)) in enumerate(zip(recs, pairs)):
+            ref = oracle_mod.port_align(mode, s1.encode(), s2.encode(), prm)
+            assert f[0] == f"r{k}" and f[2] == f"t{k}" and f[9] == s1 and f[11] == f"AS:i:{ref.score}", (mode, k)
+            if not ref.ops:
+                assert f[1] == "4" and f[5] == "*"
+                continue
+            ops = re.findall(r"(\d+)([MIDNS])", f[5])
+            assert sum(int(n) for n, c in ops if c in "MIS") == len(s1), (mode, k, f[5])
+            body = "".join(c * int(n) for n, c in ops if c != "S")
+            assert body == ref.ops.decode(), (mode, k)
+            assert int(f[3]) == (1 if mode == "global" else ref.coords[3] + 1), (mode, k)
+
+
+@pytest.mark.gpu
+def test_batch_fit_junction_lists(built, oracle_mod, tmp_path):
+    """fit -s in batch mode: every target brings its own junction list; a target header without one is an error (the
+    kseq quirk of inheriting the previous record's comment must not leak another pair's junctions); -w reads the list
+    as a whitelist."""
+    import random
+    rng = random.Random(3)
+    pairs = []
+    for k in range(30):
+        l2 = rng.randint(60, 300)
+        s2 = "".join(rng.choice("ACGT") for _ in range(l2))
+        a, b = sorted(rng.sample(range(10, l2 - 10), 2))
+        s1 = s2[max(0, a - 25):a] + s2[b:b + 25]
+        pairs.append((s1, s2, f"{a}|{b - 1}|{b}"))
+    fa = tmp_path / "j.fa"
+    _write_pairs(fa, pairs)
+    for flag, jump in (([], True), (["-w"], 2)):
+        pr = subprocess.run([CLI, "batch", "fit", "-s", "-j", "-4", "-c"] + flag + [str(fa)], capture_output=True)
+        assert pr.returncode == 0, pr.stderr[-300:]
+        rows = [r.split("\t") for r in pr.stdout.decode().strip().split("\n")]
+        for k, (s1, s2, com) in enumerate(pairs):
+            ref = oracle_mod.port_align("fit", s1.encode(), s2.encode(), oracle_mod.Params(1, -2, -5, -1, -4, jump), [int(x) for x in com.split("|")])
+            assert int(rows[k][2]) == ref.score, (flag, k)
+            assert "".join(c * int(n) for n, c in __import__("re").findall(r"(\d+)([MIDN])", rows[k][7])) == ref.ops.decode(), (flag, k)
+    bad = tmp_path / "bad.fa"
+    _write_pairs(bad, pairs[:2] + [(pairs[2][0], pairs[2][1], None)] + pairs[3:5])
+    pr = subprocess.run([CLI, "batch", "fit", "-s", str(bad)], capture_output=True)
+    assert pr.returncode == 255 and pr.stderr == b"FATAL ERROR: fail to read junction sites\n"
