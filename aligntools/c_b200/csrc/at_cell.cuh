@@ -45,6 +45,10 @@ enum { TAG_J = 0, TAG_U = 1, TAG_M = 2, TAG_L = 3 };      // tag of the winner o
 // (l1+l2+2)*max|param| < 2^25, which the host checks (validate_batch -> AT_E_RANGE).
 #define AT_NEG (-(1 << 29))
 #define AT_NEG_INIT (-(1 << 30) - (1 << 29))
+// The same inside one half of the packed s16x2 lanes (x8 domain, before the 0x8000 bias): finite values stay above
+// -24000 (host check), a -inf value lives for at most two steps next to a border before a finite candidate replaces
+// it, so its drift stays far inside [-32768, -24000).
+#define AT_NEG16 (-30000)
 
 template <bool PACKED> struct Lanes;
 

@@ -6,7 +6,8 @@
 //   Lanes<false>  int32   : one pair per warp, every mode.
 //   Lanes<true>   s16x2   : TWO pairs per warp, pair A in bits 0-15 and pair B in bits 16-31 of
 //                           every register (VIADDMNMX.U16x2 / VIMNMX3.U16x2 DPX instructions);
-//                           local mode, both pairs share l2.
+//                           every mode but fit + jump.  Both pairs share l2 (global / fit: l1 as well, so that
+//                           one lane holds the last row of both); -inf is AT_NEG16 inside the 16 bits.
 //
 // Geometry: lane k owns R consecutive rows; at step t it works on column j = t - k (anti-diagonal
 // of R-row blocks).  Per step each lane hands the last row of its strip -- M+o, L and H = max(L, M, U[, J]),
@@ -72,12 +73,14 @@ struct FillArgs2 {
 	int             twobit;  // PROF: q / t hold 2-bit codes (AT_SEQ_2BIT, four symbols per byte, byte-aligned records; *_off are byte offsets)
 };
 
+// packed lanes with up to five rows per lane (the 150-row reads of BASELINE config 2 are R = 5): hold ptxas to the 96 registers
+// that let five CTAs share an SM -- the shared-memory profile allows exactly five; the other variants to 128 / 168 / 255
 template <int MODE, int R, bool JUMP, bool PACKED, bool PROF>
-__global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillArgs2 a)
+__global__ void __launch_bounds__(32 * AT_FILL_WARPS, (PACKED && R <= 5) ? 5 : (JUMP && R > 5) ? 2 : (JUMP || R > 6) ? 3 : 4) at_fill_affine(const FillArgs2 a)
 {
 	typedef Lanes<PACKED> V;
 	typedef typename V::T T;
-	static_assert(!PACKED || (MODE == MODE_LOCAL && !JUMP), "packed lanes: local mode");
+	static_assert(!PACKED || !JUMP, "packed lanes: no jump state");
 	constexpr bool LOCAL = MODE == MODE_LOCAL;
 	constexpr uint32_t SPW = V::STEPS_PER_WORD;
 	constexpr int RPP = 32 * R;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 	const uint32_t mu8 = (uint32_t)(8 * (m >= u ? m - u : u - m)) * (PACKED ? 0x10001u : 1u);     // per half; < 1 << SHIFT (host-checked)
 	const int nsg = m >= u ? -1 : 1;                                    // s = m - penalty  (or + when u > m)
 	const T ZERO = V::value(0);
-	const T NEGV = PACKED ? ZERO : (T)AT_NEG;                           // -inf stand-in (int32 lanes only)
+	const T NEGV = PACKED ? (T)((uint32_t)(AT_NEG16 * 0x10001) + 0x80008000u) : (T)AT_NEG;      // -inf stand-in (at_cell.cuh)
 	const bool want_ptr = a.want_ptr != 0;
 	const bool twobit = PROF && a.twobit != 0;
 
@@ -232,8 +235,10 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					sa[c] = 8 * (qa == sy ? m : u); sb[c] = 8 * (qb == sy ? m : u);
 				}
 #pragma unroll
-				for (int c = 0; c < NC; ++c)      // packed: per half, two's complement (VIADDMNMX.U16x2 adds per half)
-					prof[(c * 32 + lane) * LS + r] = PACKED ? (((uint32_t)sa[c >> 2] & 0xffffu) | ((uint32_t)sb[c & 3] << 16)) : (uint32_t)sa[c];
+				for (int c = 0; c < NC; ++c)
+					prof[(c * 32 + lane) * LS + r] = !PACKED ? (uint32_t)sa[c]
+					                                 : LOCAL ? (((uint32_t)sa[c >> 2] & 0xffffu) | ((uint32_t)sb[c & 3] << 16))      // fused add: per half
+					                                         : (uint32_t)(sa[c >> 2] + sb[c & 3] * 65536);                         // plain add: exact sum
 			}
 		}
 		__syncwarp();
@@ -256,14 +261,15 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 		else if (MODE == MODE_LOCAL) { b0M = ZERO + o8 + V::rep(3); b0L = ZERO | V::rep(3); b0H = ZERO | V::rep(TAG_L); }
 		else                         { b0M = ZERO + o8 + V::rep(3); b0L = NEGV | V::rep(3); b0H = ZERO | V::rep(TAG_M); }                  // :619-624
 		if (lane) { b0M = 0; b0L = 0; b0H = 0; b0E = 0; }
-		const int cap_r = (!PACKED && lane == (int)((l1A - 1) / R)) ? (int)((l1A - 1) % R) : -1;
+		const int cap_r = (!LOCAL && lane == (int)((l1A - 1) / R)) ? (int)((l1A - 1) % R) : -1;      // packed global / fit jobs: l1A == l1B
 		int hot[R];
 #pragma unroll
 		for (int r = 0; r < R; ++r) hot[r] = r == cap_r ? 1 : 0;
 		T kbest = PACKED ? (T)0 : (T)AT_NEG_INIT;     // below every real key
 		T tbest = 0;
-		int capM = AT_NEG_INIT, capMj = 0, capL = AT_NEG_INIT, capLj = 0;      // fit
-		int gH = 0;                                                            // global
+		int capM = AT_NEG_INIT, capMj = 0, capL = AT_NEG_INIT, capLj = 0;      // fit, int32 lanes
+		T capM2 = 0, capL2 = 0, capMj2 = 0, capLj2 = 0;                        // fit, packed lanes (biased: 0 is below every value)
+		T gH = 0;                                                              // global
 
 		// first step at which the running key took its (so far) final value -> column of the running maximum
 		auto note_best = [&](const T before, const T after, const uint32_t t) {
@@ -272,7 +278,10 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 		};
 		// one step of the systolic array.  ring_k: PROF, unchecked: address of the column's ring entry (a constant offset
 		// from the word's base); mul / mulj: see cell_update
-		auto step = [&](const uint32_t t, const bool checked, const uint16_t *ring_k, const uint32_t mul, const uint32_t mulj) {
+		// tail: unchecked steps past the last column.  Cells of columns > l2 are computed like any other (on whatever the
+		// ring holds there): no cell of the matrix depends on them, their pointers are never read and the end-cell
+		// searches test the column -- only local mode's running maximum must not see them.
+		auto step = [&](const uint32_t t, const bool checked, const uint16_t *ring_k, const uint32_t mul, const uint32_t mulj, const bool tail) {
 			const int j = (int)t - lane;
 			// neighbour's last row, or matrix row 0 at column j = t in lane 0 (multiply-add: keeps the ALU pipe free)
 			const T rM = __shfl_up_sync(0xffffffffu, sM, 1) * nz + b0M;
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					}
 				}
 				T lup = rL, mo_up = rM;
-				int rowM = 0, rowL = 0;                        // fit: M, L of the pair's last row
+				T rowM = 0, rowL = 0;                          // fit: M, L of the pair's last row
 				const T kold = kbest;
 				CellOut<PACKED> out;
 #pragma unroll
@@ -317,15 +326,25 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 					if (LOCAL) kbest = V::addmax(out.mk, crow[r], kbest);
 					// fit: the pair's last row is row cap_r of ONE lane: pick its values with a one-hot multiply-add per
 					// row (FMA pipe) instead of compares and selects in every row; the search itself runs once per step
-					if (MODE == MODE_FIT) { rowM += (int)out.mk * hot[r]; rowL += (int)out.lk * hot[r]; }
-					if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) gH = (int)out.h; }   // (cheaper than the one-hot form here)
+					if (MODE == MODE_FIT) { rowM += out.mk * (T)hot[r]; rowL += out.lk * (T)hot[r]; }
+					if (MODE == MODE_GLOBAL) { if (r == cap_r && j == (int)l2) gH = out.h; }   // (cheaper than the one-hot form here)
 				}
 				sM = out.mo; sL = out.lk; sH = out.h;
-				if (MODE == MODE_FIT && cap_r >= 0 && j < (int)l2) {       // column l2 excluded (:677, :684)
-					rowM &= ~7; rowL &= ~7;                                // drop the tags: M and L are compared with each other at the end
-					if (rowM > capM) { capM = rowM; capMj = j; }
-					if (rowL > capL) { capL = rowL; capLj = j; }
+				if (MODE == MODE_FIT && !PACKED && cap_r >= 0 && j < (int)l2) {       // column l2 excluded (:677, :684)
+					const int rm = (int)rowM & ~7, rl = (int)rowL & ~7;               // drop the tags: M and L are compared with each other at the end
+					if (rm > capM) { capM = rm; capMj = j; }
+					if (rl > capL) { capL = rl; capLj = j; }
 				}
+				if (MODE == MODE_FIT && PACKED) {      // both pairs at once; lanes without the last row carry 0, which never wins
+					const bool in = j >= 1 && j < (int)l2;
+					const T rm = in ? (rowM & ~V::rep(7)) : (T)0, rl = in ? (rowL & ~V::rep(7)) : (T)0;
+					const T j2 = (T)((uint32_t)j * 0x10001u);
+					const T nm = V::vmax(capM2, rm), nl = V::vmax(capL2, rl);         // strictly greater only: the smallest column among maxima
+					const T cm = (T)__vminu2((uint32_t)(nm ^ capM2), 0x10001u) * 0xffffu, cl = (T)__vminu2((uint32_t)(nl ^ capL2), 0x10001u) * 0xffffu;
+					capMj2 = (capMj2 & ~cm) | (j2 & cm); capLj2 = (capLj2 & ~cl) | (j2 & cl);
+					capM2 = nm; capL2 = nl;
+				}
+				if (LOCAL && tail) kbest = j > (int)l2 ? kold : kbest;
 				if (LOCAL) note_best(kold, kbest, t);
 			} else {
 #pragma unroll
@@ -339,18 +358,26 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 				load_block(tb / 256u + 1u);
 				__syncwarp();
 			}
-			if (tb >= 32u && tb + SPW - 1u <= l2) {
+			if (tb >= 32u) {      // every lane is inside the matrix or past its last column: no range checks
 				const uint16_t *rb = ring16 + ((tb - (uint32_t)lane - 1u) & (AT_RING - 1));      // column j - 1 of step tb; + k for step tb + k (mirrored tail)
-				if (PACKED) {
+				if (tb + SPW - 1u <= l2) {
+					if (PACKED) {
 #pragma unroll
-					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, rb + k, k == 0 ? 0u : 16u, 2u);
-				} else {      // int32 lanes: 8 steps per word; unroll by 4 only (instruction-cache footprint)
+						for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, rb + k, k == 0 ? 0u : 16u, 2u, false);
+					} else {      // int32 lanes: 8 steps per word; unroll by 4 only (instruction-cache footprint)
 #pragma unroll 4
-					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, rb + k, 16u, 2u);
+						for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, rb + k, 16u, 2u, false);
+					}
+				} else if (PACKED) {      // the last ~32 steps: some lanes are past column l2
+#pragma unroll
+					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, rb + k, k == 0 ? 0u : 16u, 2u, true);
+				} else {
+#pragma unroll 2
+					for (uint32_t k = 0; k < SPW; ++k) step(tb + k, false, rb + k, 16u, 2u, true);
 				}
 			} else {
 #pragma unroll 1
-				for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true, nullptr, (PACKED && k == 0) ? 0u : 16u, 2u);
+				for (uint32_t k = 0; k < SPW; ++k) step(tb + k, true, nullptr, (PACKED && k == 0) ? 0u : 16u, 2u, false);
 			}
 			if (want_ptr) {
 				uint32_t *w = ptr + ((size_t)(tb / SPW) * 32 + lane) * R;
@@ -386,11 +413,19 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS) at_fill_affine(const FillA
 		} else {
 			const int owner = (int)((l1A - 1) / R);
 			if (lane == owner) {
-				if (MODE == MODE_GLOBAL) { a.score[pA] = gH >> 3; a.end_i[pA] = l1A; a.end_j[pA] = l2; a.end_state[pA] = (uint8_t)(3 - (gH & 3)); }
-				else {
-					const bool useL = capL > capM;            // L replaces M only when strictly greater (:685)
-					a.score[pA] = (useL ? capL : capM) >> 3; a.end_i[pA] = l1A; a.end_j[pA] = useL ? capLj : capMj;
-					a.end_state[pA] = useL ? ST_LOW : ST_MID;
+#pragma unroll
+				for (int h = 0; h < (PACKED ? 2 : 1); ++h) {
+					const uint32_t p = h ? pB : pA;
+					if (h && pB == pA) break;
+					auto half = [&](T v) -> int { return PACKED ? (int)(((uint32_t)v >> (16 * h)) & 0xffffu) - 0x8000 : (int)v; };
+					if (MODE == MODE_GLOBAL) { const int g = half(gH); a.score[p] = g >> 3; a.end_i[p] = l1A; a.end_j[p] = l2; a.end_state[p] = (uint8_t)(3 - (g & 3)); }
+					else {
+						const int cM = PACKED ? half(capM2) : capM, cL = PACKED ? half(capL2) : capL;
+						const int jM = PACKED ? (int)(((uint32_t)capMj2 >> (16 * h)) & 0xffffu) : capMj, jL = PACKED ? (int)(((uint32_t)capLj2 >> (16 * h)) & 0xffffu) : capLj;
+						const bool useL = cL > cM;            // L replaces M only when strictly greater (:685)
+						a.score[p] = (useL ? cL : cM) >> 3; a.end_i[p] = l1A; a.end_j[p] = useL ? jL : jM;
+						a.end_state[p] = useL ? ST_LOW : ST_MID;
+					}
 				}
 			}
 		}

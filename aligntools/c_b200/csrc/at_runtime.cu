@@ -537,9 +537,13 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	if (const char *env = getenv("AT_PTR_BUDGET_MB")) budget_words = (uint64_t)atoll(env) * (1ull << 20) / 4;
 	// packed s16x2 lanes (two pairs per warp): local mode, scores x8 must fit int16, 8|m-u| < 256 (symbols are << 8)
 	const int64_t maxabs = std::max<int64_t>({llabs((long long)b->prm.m), llabs((long long)b->prm.u), llabs((long long)b->prm.o), llabs((long long)b->prm.e), 1});
-	const bool p16_mode = b->mode == AT_LOCAL && llabs((long long)b->prm.m - b->prm.u) <= 31 && !getenv("AT_NO_P16");
+	// global / fit (without jump state) also carry -inf inside the 16 bits (AT_NEG16 = -30000, at_cell.cuh): finite values must
+	// stay above -24000 and a -inf value may drift by a few steps' worth of the largest parameter
+	const bool p16_local = b->mode == AT_LOCAL;
+	const bool p16_mode = (p16_local || b->mode == AT_GLOBAL || (b->mode == AT_FIT && !jump)) && llabs((long long)b->prm.m - b->prm.u) <= 31 &&
+	                      (p16_local || maxabs <= 31) && !getenv("AT_NO_P16");
 	auto p16_ok = [&](uint32_t l1, uint32_t l2) {
-		return p16_mode && l1 <= 32u * MAXR && l2 <= 60000u && 8 * (int64_t)(l1 + l2 + 2) * maxabs < 32000;
+		return p16_mode && l1 <= 32u * MAXR && l2 <= 60000u && 8 * (int64_t)(l1 + l2 + 42) * maxabs < (p16_local ? 32000 : 24000);      // + 40: K1 also computes up to 34 columns past l2
 	};
 	release_chunks(s);      // a pipeline worker reuses its shard (and the shard-level buffers) for every sub-slice
 	uint64_t max_chunk_words = 0, max_scratch_words = 0;
@@ -580,7 +584,8 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		}
 		// ---- packed jobs (K1, s16x2): partners must share the rows-per-lane class and l2 ----
 		{
-			auto key = [&](uint32_t k) { return ((uint64_t)s.h_rclass[k] << 32) | in->t_len[s.p0 + k]; };
+			// local: the partners share the rows-per-lane class and l2; global / fit: l1 as well (one lane holds the last row of both)
+			auto key = [&](uint32_t k) { return ((uint64_t)(p16_local ? s.h_rclass[k] : in->q_len[s.p0 + k]) << 32) | in->t_len[s.p0 + k]; };
 			bool sorted = true;
 			for (size_t x = 1; x < cand.size() && sorted; ++x) sorted = key(cand[x - 1]) >= key(cand[x]);
 			if (!sorted) std::stable_sort(cand.begin(), cand.end(), [&](uint32_t x, uint32_t y) { return key(x) > key(y); });
@@ -736,7 +741,8 @@ static int validate_batch(at_handle *h, int mode, const at_params *p, const at_b
 		if (l1 == 0 || l2 == 0) { if (report) set_err(h, "pair %llu: empty record", (unsigned long long)k); return AT_E_UNDEF; }
 		if (mode == AT_FIT && l1 > l2) { if (report) set_err(h, "pair %llu: first sequence must be shorter than the second to do fitting alignment", (unsigned long long)k); return AT_E_FITLEN; }
 		if (mode == AT_FIT && l2 < 2) { if (report) set_err(h, "pair %llu: fit with l2 < 2 is undefined in the reference", (unsigned long long)k); return AT_E_UNDEF; }
-		if (l1 + l2 + 2 > max_sum) { if (report) set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
+		/* + 40: K1's lanes run up to 34 columns past l2 (their cells obey the same bounds) */
+		if (l1 + l2 + 42 > max_sum) { if (report) set_err(h, "pair %llu: score range", (unsigned long long)k); return AT_E_RANGE; }
 		return AT_OK;
 	};
 	// ranges of pairs: checks and the range's cell total in one pass (a few host threads on a large batch),
@@ -858,7 +864,7 @@ extern "C" int at_batch_create(at_handle *h, int mode, const at_params *p, const
 
 // ------------------------------------------------------------------ launch ----
 // Kernel tables.  K1 (at_fill_affine): mode variant x rows-per-lane x lanes; kind: 0 global, 1 local,
-// 2 fit, 3 fit+jump on int32 lanes, 4 local on packed s16x2 lanes.  K2 (at_wave_*): affine modes
+// 2 fit, 3 fit+jump on int32 lanes, 4 / 5 / 6 local / global / fit on packed s16x2 lanes.  K2 (at_wave_*): affine modes
 // with R = 8, single-plane modes (overlap / edit) with R = 1..8.
 typedef void (*fill2_fn)(const FillArgs2);
 typedef void (*wave_fn)(const WaveArgs);
@@ -870,7 +876,9 @@ template <int R, bool PROF> static fill2_fn affine_fn(int kind)
 	case 1: return at_fill_affine<MODE_LOCAL, R, false, false, PROF>;
 	case 2: return at_fill_affine<MODE_FIT, R, false, false, PROF>;
 	case 3: return at_fill_affine<MODE_FIT, R, true, false, PROF>;
-	default: return at_fill_affine<MODE_LOCAL, R, false, true, PROF>;
+	case 4: return at_fill_affine<MODE_LOCAL, R, false, true, PROF>;
+	case 5: return at_fill_affine<MODE_GLOBAL, R, false, true, PROF>;
+	default: return at_fill_affine<MODE_FIT, R, false, true, PROF>;
 	}
 }
 template <bool PROF> static fill2_fn affine_kernel_r(int kind, int R)
@@ -940,7 +948,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 		for (size_t li = 0; li < c.launches.size(); ++li) {
 			Launch &l = c.launches[li];
 			const void *fn = l.kind == LK_BITS ? (const void *)bits_kernel(l.r) : l.kind == LK_WAVE ? (const void *)wave_kernel(b->mode, jump, l.r, s.prof)
-			                                   : (const void *)affine_kernel(l.kind == LK_PACKED ? 4 : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode), l.r, s.prof);
+			                                   : (const void *)affine_kernel(l.kind == LK_PACKED ? (b->mode == AT_LOCAL ? 4 : b->mode == AT_GLOBAL ? 5 : 6) : (b->mode == AT_FIT ? (jump ? 3 : 2) : b->mode), l.r, s.prof);
 			const int warps = l.kind >= LK_WAVE ? AT_WAVE_WARPS : AT_FILL_WARPS;
 			const size_t dyn_smem = l.kind >= LK_WAVE ? 0 : fill_smem_bytes(l.r, l.kind == LK_PACKED, s.prof);
 			if (dyn_smem > 48 * 1024) CU(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));

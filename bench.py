@@ -310,7 +310,7 @@ def time_config(al, A, w, name, flags, steps, warmup, e2e_steps, peaks, barrier,
     return out, raw
 
 
-def sharded_leg(al, A, dist, w, name, flags, rank, world, steps, barrier, expect=None):
+def sharded_leg(al, A, dist, w, name, flags, rank, world, steps, barrier, expect=None, twobit=False):
     """ONE batch, contiguous slices balanced by DP cells (at_plan_slices), each rank aligns its slice through
     at_batch_align with host buffers, results land in rank 0's host memory; all of it inside the clock."""
     n = len(w["q_len"])
@@ -328,8 +328,16 @@ def sharded_leg(al, A, dist, w, name, flags, rank, world, steps, barrier, expect
     hg = HostGather(dist, rank, world, n, cap, name)
     keep = []
     arrs = {}
-    for k in ("q", "t"):
-        arrs[k], t_ = pinned_like(w[k]); keep.append(t_)
+    enc = A.SEQ_BYTES
+    q_off, t_off = w["q_off"], w["t_off"]
+    if twobit:      # the library's input encoding for ACGT data: a quarter of the PCIe bytes, read by the fill as it is
+        enc = A.SEQ_2BIT
+        q2, q_off, _ = A.pack_2bit(w["q"], w["q_off"], w["q_len"], align=16)
+        t2, t_off, _ = A.pack_2bit(w["t"], w["t_off"], w["t_len"], align=16)
+        arrs["q"], k1 = pinned_like(q2); arrs["t"], k2 = pinned_like(t2); keep += [k1, k2]
+    else:
+        for k in ("q", "t"):
+            arrs[k], t_ = pinned_like(w[k]); keep.append(t_)
     so = w["site_off"][lo:hi + 1] if w.get("site_off") is not None else None
     outb = hg.slice_out(lo, hi)
     full_cigar = np.zeros(cap * world + 1, np.uint32) if (rank == 0 and tb) else None
@@ -340,8 +348,8 @@ def sharded_leg(al, A, dist, w, name, flags, rank, world, steps, barrier, expect
         barrier()
         t1 = time.perf_counter()
         if hi > lo:
-            al.align_arrays(w["mode"], opt, arrs["q"], w["q_off"][lo:hi], w["q_len"][lo:hi], arrs["t"], w["t_off"][lo:hi], w["t_len"][lo:hi],
-                            sites=w.get("sites"), site_off=so, out_flags=flags, out=outb, cigar_cap=cap if tb else None)
+            al.align_arrays(w["mode"], opt, arrs["q"], q_off[lo:hi], w["q_len"][lo:hi], arrs["t"], t_off[lo:hi], w["t_len"][lo:hi],
+                            sites=w.get("sites"), site_off=so, out_flags=flags, encoding=enc, out=outb, cigar_cap=cap if tb else None)
         barrier()                                   # every slice is in host memory
         if rank == 0 and tb:
             total_ops = hg.merge(cut, full_cigar, full_off)
@@ -361,6 +369,7 @@ def sharded_leg(al, A, dist, w, name, flags, rank, world, steps, barrier, expect
         out = {"name": name, "pairs_total": n, "pairs_per_gpu": [int(cut[r + 1] - cut[r]) for r in range(world)], "cells": cells,
                "value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps, "scaling": "strong",
                "gather": "rank 0 host memory (shared-memory output arrays; CIGARs concatenated in pair order), inside the clock",
+               "encoding": "2bit" if twobit else "bytes",
                "checks": {"score_sum": score_sum, "cigar_ops": int(total_ops)}}
         if expect is not None:
             assert score_sum == expect["score_sum"], f"sharded {name}: score checksum differs from the single-GPU run"
@@ -534,7 +543,7 @@ def main():
         sharded = []
         w_all = w if world == 1 else make_workload(args.pairs, 0)          # every rank generates the SAME batch
         s2 = sharded_leg(al, A, dist, w_all, "C2 1 Mi pairs in total" if args.pairs == 1 << 20 else f"C2 {args.pairs} pairs in total", A.OUT_CIGAR,
-                         rank, world, 3, barrier, expect={"score_sum": score_sum, "cigar_ops": cigar_ops} if world == 1 else None)
+                         rank, world, 3, barrier, expect={"score_sum": score_sum, "cigar_ops": cigar_ops} if world == 1 else None, twobit=not args.bytes_e2e)
         w5 = synth.config5_edit(n_pairs=64, stream=0)
         s5 = sharded_leg(al, A, dist, w5, "C5 64 pairs in total", 0, rank, world, 2, barrier)
         if rank == 0:

@@ -36,7 +36,7 @@ static void fill(PairIO *pp /* 1 or 2 pairs, same l2 */, int m, int u, int o, in
 	for (int h = 0; h < NP; ++h) { if (pp[h].l1 > l1) l1 = pp[h].l1; pp[h].nib.assign((size_t)(pp[h].l1 + 1) * (l2 + 1), 0xff); pp[h].jbit.assign((size_t)(pp[h].l1 + 1) * (l2 + 1), 0); }
 	CellConst<PACKED> c;
 	c.set(o, e, jp, cell_k_and<PACKED>(), cell_k_or<PACKED>());
-	const T ZERO = V::value(0), NEGV = PACKED ? ZERO : (T)AT_NEG;
+	const T ZERO = V::value(0), NEGV = PACKED ? (T)((uint32_t)(AT_NEG16 * 0x10001) + 0x80008000u) : (T)AT_NEG;
 	std::vector<RowState<PACKED, JUMP>> row(l1 + 1);
 	std::vector<T> lcol0(l1 + 1);      // L(i, 0): what row i hands down in column 0 (only used through lup of column >= 1? no: L flows within a column)
 	// column 0 (left border) -- reference: :432-436 global, calloc zeros local, :612-617 fit
@@ -190,8 +190,10 @@ extern "C" int cell_model_run(int mode, int jump, int packed, const uint8_t *s1a
 		return 0;
 	}
 	if (packed) {
-		if (mode != MODE_LOCAL || jump) return -1;
-		fill<MODE_LOCAL, false, true>(pp, m, u, o, e, jp, 0);
+		if (jump) return -1;
+		if (mode == MODE_LOCAL) fill<MODE_LOCAL, false, true>(pp, m, u, o, e, jp, 0);
+		else if (mode == MODE_GLOBAL) fill<MODE_GLOBAL, false, true>(pp, m, u, o, e, jp, 0);
+		else fill<MODE_FIT, false, true>(pp, m, u, o, e, jp, 0);
 	} else if (mode == MODE_GLOBAL) fill<MODE_GLOBAL, false, false>(pp, m, u, o, e, jp, 0);
 	else if (mode == MODE_LOCAL) fill<MODE_LOCAL, false, false>(pp, m, u, o, e, jp, 0);
 	else if (mode == MODE_FIT && jump) fill<MODE_FIT, true, false>(pp, m, u, o, e, jp, 0);

@@ -87,20 +87,22 @@ def test_int32_lanes_vs_oracle(model, oracle_mod, mode):
         assert got["ops"] == ref.ops, (mode, k, prm, s1, s2, sites)
 
 
-def test_packed_lanes_vs_oracle(model, oracle_mod):
-    """Two pairs in the halves of every register (local mode, shared l2, different reads / read lengths)."""
-    rng = random.Random(77)
+@pytest.mark.parametrize("mode", ["local", "global", "fit"])
+def test_packed_lanes_vs_oracle(model, oracle_mod, mode):
+    """Two pairs in the halves of every register (shared l2, different reads / read lengths); global and fit carry
+    -inf as AT_NEG16 inside the 16 bits."""
+    rng = random.Random(77 + len(mode))
     for k in range(700):
         l2 = rng.randint(2, 160)
-        s1a, s2a = rand_pair(rng, 70, 160, False, l2=l2)
-        s1b, s2b = rand_pair(rng, 70, 160, False, l2=l2)
+        s1a, s2a = rand_pair(rng, 70, 160, mode == "fit", l2=l2)
+        s1b, s2b = rand_pair(rng, 70, 160, mode == "fit", l2=l2)
         prm = rand_params(rng, flipped=(k % 4 == 3))
-        if 8 * (max(len(s1a), len(s1b)) + l2 + 2) * max(abs(v) for v in prm.values()) >= 32000:
+        if 8 * (max(len(s1a), len(s1b)) + l2 + 2) * max(abs(v) for v in prm.values()) >= 24000:
             continue
         p = oracle_mod.Params(prm["m"], prm["u"], prm["o"], prm["e"], prm["j"], False)
-        got = run_model(model, "local", False, True, s1a, s1b, s2a, s2b, prm, None)
+        got = run_model(model, mode, False, True, s1a, s1b, s2a, s2b, prm, None)
         for h, (s1, s2) in enumerate(((s1a, s2a), (s1b, s2b))):
-            ref = oracle_mod.port_align("local", s1, s2, p)
+            ref = oracle_mod.port_align(mode, s1, s2, p)
             assert got[h]["score"] == ref.score, (k, h, prm, s1, s2)
             assert got[h]["end"] == tuple(ref.coords[:2]) and got[h]["beg"] == tuple(ref.coords[2:]), (k, h, prm)
             assert got[h]["ops"] == ref.ops, (k, h, prm, s1, s2)

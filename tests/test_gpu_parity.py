@@ -472,3 +472,41 @@ def test_junction_whitelist_mode(A, aligner, oracle_mod):
     # and the same list as a blacklist gives different alignments (the modes are not confused)
     res_b = aligner.align("fit", q[:40], t[:40], A.Opt(**prm, jump=True), sites=[ss[so[k]:so[k + 1]] for k in range(40)])
     assert any(res_b.aln(k) != res.aln(k) for k in range(40))
+
+
+@pytest.mark.parametrize("mode", ["global", "fit"])
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"ACDEFGHIKLMNPQRSTVWY"])
+def test_k1_packed_lanes_global_and_fit(A, aligner, oracle_mod, mode, alphabet):
+    """Global and fit on packed s16x2 lanes (two pairs per warp when they share l1 and l2; -inf is AT_NEG16 inside the
+    16 bits): uniform shapes of every rows-per-lane class, query-profile and xor/min variants, sign-flipped parameters,
+    against the oracle -- and a batch whose score range does not fit 16 bits, which must fall back to int32 lanes."""
+    rng = random.Random(606 + len(alphabet) + len(mode))
+    for shape_k, (l1, l2) in enumerate([(150, 150), (150, 400), (31, 64), (97, 97), (200, 333), (256, 256), (1, 9)]):
+        if mode == "fit" and l1 > l2:
+            continue
+        q, t = [], []
+        for _ in range(37):
+            s2 = bytes(rng.choice(alphabet) for _ in range(l2))
+            st = rng.randrange(0, l2 - l1 + 1)
+            s1 = bytearray(c if rng.random() > 0.1 else rng.choice(alphabet) for c in s2[st:st + l1])
+            if rng.random() < 0.5 and l1 > 20:      # an indel, keeping the length
+                k = rng.randrange(5, l1 - 5)
+                del s1[k]; s1.append(rng.choice(alphabet))
+            q.append(bytes(s1)); t.append(s2)
+        qb, qo, ql = pack_batch(q)
+        tb, to, tl = pack_batch(t)
+        prms = [dict(m=1, u=-1, o=-4, e=-1, j=-10, jump=False), dict(m=2, u=-3, o=-5, e=-2, j=-10, jump=False)]
+        if shape_k < 3:
+            prms.append(dict(m=2, u=-1, o=1, e=-1, j=-10, jump=False))      # a profitable gap opening
+        for prm in prms:
+            tm = check_batch_vs_port(A, aligner, oracle_mod, mode, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl)
+            if 8 * (l1 + l2 + 2) * max(abs(v) for k, v in prm.items() if k in "muoe") < 24000:
+                assert tm.fill_kernel_kind == 1, "expected packed s16x2 lanes"
+    # too wide a score range for 16 bits: int32 lanes, same answers
+    l1, l2 = 250, 900
+    q = [bytes(rng.choice(alphabet) for _ in range(l1)) for _ in range(8)]
+    t = [bytes(rng.choice(alphabet) for _ in range(l2)) for _ in range(8)]
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    tm = check_batch_vs_port(A, aligner, oracle_mod, mode, dict(m=5, u=-4, o=-9, e=-3, j=-10, jump=False), qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl)
+    assert tm.fill_kernel_kind == 0
