@@ -30,7 +30,7 @@ EXPORTS = ["at_default_params", "at_strerror", "at_version", "at_create", "at_de
            "at_device_count", "at_launch_count", "at_align_gla", "at_align_local_affine",
            "at_align_fit_affine_jump", "at_align_overlap", "at_edit_dist", "at_batch_create",
            "at_batch_run", "at_batch_sizes", "at_batch_fetch", "at_batch_free", "at_batch_align",
-           "at_pack_2bit", "at_cigar_to_string", "at_plan_slices", "at_host_alloc", "at_host_free"]
+           "at_pack_2bit", "at_cigar_to_string", "at_plan_slices", "at_host_alloc", "at_host_free", "at_host_register", "at_host_unregister"]
 
 
 class AtError(RuntimeError):
@@ -111,6 +111,11 @@ def load_library():
     lib.at_cigar_to_string.restype = C.c_int64
     lib.at_cigar_to_string.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
     lib.at_plan_slices.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    lib.at_host_alloc.restype = C.c_void_p
+    lib.at_host_alloc.argtypes = [C.c_size_t]
+    lib.at_host_free.argtypes = [C.c_void_p]
+    lib.at_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.at_host_unregister.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 

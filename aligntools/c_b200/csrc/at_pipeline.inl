@@ -15,7 +15,7 @@ static uint64_t pipe_slice_cells() { return env_u64("AT_PIPE_SLICE_CELLS", 1ull 
 struct PipeSlice { uint64_t lo = 0, hi = 0; size_t dev = 0; uint64_t tot_ops = 0, tot_cols = 0; bool known = false; };
 
 static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_batch_input *in, uint32_t out_flags,
-                           at_batch_output *out, at_timing *timing, const std::vector<uint64_t> &prefix)
+                           at_batch_output *out, at_timing *timing, const std::vector<uint64_t> &prefix, uint64_t slice_cells)
 {
 	const uint64_t total_cells = prefix[in->n_pairs];
 	const auto t_func = std::chrono::steady_clock::now();
@@ -30,7 +30,7 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 		const uint64_t cells = prefix[dcut[d + 1]] - prefix[dcut[d]];
 		// graduated sub-slices: quarter-size units, grouped 1, 2, 4, 4, 4, ... so that the first kernel starts
 		// early (short first upload) while the bulk runs in full-size sub-slices (fewer kernel tails)
-		size_t units = (size_t)std::max<uint64_t>(1, 4 * cells / pipe_slice_cells());
+		size_t units = (size_t)std::max<uint64_t>(1, (unsigned __int128)4 * cells / slice_cells);
 		units = std::min<size_t>(units, 256);
 		units = std::min<size_t>(units, (size_t)(dcut[d + 1] - dcut[d]));
 		std::vector<uint64_t> cut;
@@ -175,12 +175,30 @@ extern "C" int at_batch_align(at_handle *h, int mode, const at_params *p, const 
 	const auto t_entry = std::chrono::steady_clock::now();
 	std::unique_lock<std::mutex> one_at_a_time(h->align_mu);      // the handle's pipeline workspaces serve one call at a time
 	std::vector<uint64_t> &prefix = h->pipe_prefix;
-	if (int rc = validate_batch(h, mode, p, in, &prefix)) return rc;
+	uint64_t wave_tasks = 0;
+	if (int rc = validate_batch(h, mode, p, in, &prefix, &wave_tasks)) return rc;
 	const uint64_t cells = prefix[in->n_pairs];
-	if (cells >= pipe_min_cells() && in->n_pairs >= 16 && !getenv("AT_NO_PIPELINE")) {
+	// Sub-slice size: about 2^33 cells (5 ms of fill) for short pairs; where the pairs run as K2 tasks (stripes of 256 rows,
+	// one warp each) a sub-slice must still hold several waves of them -- a launch with fewer tasks than resident warps
+	// leaves SMs idle and its stripe pipelines never fill.  A batch that gives fewer than two such sub-slices is not cut up.
+	uint64_t slice_cells = pipe_slice_cells();
+	bool worth = cells >= pipe_min_cells() && in->n_pairs >= 16;
+	if (wave_tasks) {
+		uint64_t min_tasks = 0;
+		for (auto &d : h->devs) min_tasks = std::max<uint64_t>(min_tasks, 4ull * 16 * d.sm_count);      // four waves of 16 warps per SM
+		min_tasks = env_u64("AT_PIPE_MIN_TASKS", min_tasks);
+		const uint64_t per_dev = wave_tasks / h->devs.size();
+		if (per_dev < 2 * min_tasks) worth = false;
+		else slice_cells = std::max<uint64_t>(slice_cells, (uint64_t)((double)cells / (double)wave_tasks * (double)min_tasks));
+	}
+	// A batch not worth cutting up but still sizeable (a few hundred long pairs, say) runs as ONE sub-slice per device through the
+	// same machinery: the workers' workspaces keep their pointer arena and buffers from call to call, where a fresh at_batch
+	// asks the driver for its arena and for the free-memory figure every time (10-25 ms on C3 / C4-sized calls).
+	const bool one_slice = !worth && cells >= env_u64("AT_ONE_SLICE_MIN_CELLS", 1ull << 28);
+	if ((worth || one_slice) && !getenv("AT_NO_PIPELINE")) {
 		if (getenv("AT_PIPE_TRACE")) fprintf(stderr, "[at pipe] validation + cell count of %llu pairs: %.2f ms\n", (unsigned long long)in->n_pairs,
 		                                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
-		return align_pipelined(h, mode, p, in, out_flags, out, timing, prefix);
+		return align_pipelined(h, mode, p, in, out_flags, out, timing, prefix, one_slice ? UINT64_MAX / 8 : slice_cells);
 	}
 	// small batches: the plain three-call path, still under the handle's lock (include/aligntools_b200.h: a handle
 	// serves one batch operation at a time; concurrent callers of at_batch_align are serialised)

@@ -117,7 +117,7 @@ extern "C" int at_create(const int *devices, int n_devices, at_handle **out)
 		// SM runs kernels of different carve-outs only one after the other, so without this every small
 		// kernel of the pipelined path would wait for a persistent fill grid of another stream to drain.
 		const void *helpers[] = {(const void *)at_traceback_walk<true>, (const void *)at_traceback_emit<true>, (const void *)at_scan_offsets,
-		                         (const void *)at_symbol_set, (const void *)at_build_jmask, (const void *)at_unpack_2bit};
+		                         (const void *)at_symbol_set, (const void *)at_build_jmask, (const void *)at_unpack_2bit, (const void *)at_plan_uniform};
 		for (const void *fn : helpers) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		h->devs.push_back(d);
 	}
@@ -167,7 +167,8 @@ struct Launch {
 	std::vector<WaveTask> h_tasks;      // LK_WAVE: (pair, stripe), pair-major
 	DevBuf<WaveTask> d_tasks;
 	uint64_t prog_base = 0;             // first progress word of this launch in Shard::d_prog
-	size_t n_jobs() const { return kind >= LK_WAVE ? h_tasks.size() : h_jobs.size(); }
+	size_t n_planned = 0;               // uniform shards: the job list exists on the device only (at_plan_uniform)
+	size_t n_jobs() const { return n_planned ? n_planned : (kind >= LK_WAVE ? h_tasks.size() : h_jobs.size()); }
 };
 
 struct Chunk {
@@ -219,10 +220,35 @@ struct Shard {
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t evk[2] = {nullptr, nullptr};
 	cudaEvent_t ev_up = nullptr;               // behind this shard's sequence upload (pipelined path: orders the sub-slices' copies)
+	cudaEvent_t ev_sync = nullptr;             // shard_sync(): a sleeping wait for the stream
 	// last-run timing
 	double fill_ms = 0, tb_ms = 0, dev_ms = 0, domk_ms = 0; uint64_t domk_cells = 0, launches = 0; uint32_t domk_kind = 0, domk_r = 0, domk_flags = 0;
 	int rc = AT_OK;
 };
+
+// How host threads wait for the device.  Spinning (the device's yield flag) has the lowest latency and is right when every
+// process has cores to spare; on a box where several ranks share few cores (one process per GPU, three pipeline workers
+// each) spinning waiters take the cores the workers need, so there the waits sleep on events created with
+// cudaEventBlockingSync.  AT_SYNC=block|spin overrides; default: block when LOCAL_WORLD_SIZE ranks leave < 6 cores each.
+static bool wait_blocking()
+{
+	static const bool v = [] {
+		if (const char *e = getenv("AT_SYNC")) return e[0] == 'b' || e[0] == 'B';
+		const char *lw = getenv("LOCAL_WORLD_SIZE");
+		const unsigned ranks = lw ? (unsigned)std::max(1, atoi(lw)) : 1u;
+		const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+		return cores / ranks < 6;
+	}();
+	return v;
+}
+static cudaError_t event_create_timed(cudaEvent_t *e) { return cudaEventCreateWithFlags(e, wait_blocking() ? cudaEventBlockingSync : cudaEventDefault); }
+static cudaError_t shard_sync(Shard &s)
+{
+	if (!wait_blocking()) return cudaStreamSynchronize(s.stream);
+	if (!s.ev_sync) { cudaError_t e = cudaEventCreateWithFlags(&s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+	cudaError_t e = cudaEventRecord(s.ev_sync, s.stream);
+	return e != cudaSuccess ? e : cudaEventSynchronize(s.ev_sync);
+}
 
 struct at_batch {
 	at_handle *h = nullptr;
@@ -345,6 +371,7 @@ static void free_shard(Shard &s)
 	for (auto &e : s.ev) if (e) cudaEventDestroy(e);
 	for (auto &e : s.evk) if (e) cudaEventDestroy(e);
 	if (s.ev_up) cudaEventDestroy(s.ev_up);
+	if (s.ev_sync) cudaEventDestroy(s.ev_sync);
 	s.cache.flush(s.stream);
 	tl_cache = nullptr; tl_big = nullptr;
 }
@@ -366,7 +393,7 @@ static int scan_alphabet(at_handle *h, Shard &s, const uint8_t *d_bytes, uint64_
 	CU(h, cudaGetLastError());
 	h->launches++;
 	CU(h, cudaMemcpyAsync(set8, s.d_symset.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-	CU(h, cudaStreamSynchronize(st));
+	CU(h, shard_sync(s));
 	return AT_OK;
 }
 
@@ -453,12 +480,12 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	// AT_PIPE_TRACE=2: host timeline of this function's phases (ms since entry) on stderr
 	static const bool trace_setup = getenv("AT_PIPE_TRACE") && atoi(getenv("AT_PIPE_TRACE")) >= 2;
 	const auto t_enter = std::chrono::steady_clock::now();
-	std::string tl;
+	std::string tl_;
 	auto mark = [&](const char *what) {
 		if (!trace_setup) return;
 		char buf[64];
 		snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
-		tl += buf;
+		tl_ += buf;
 	};
 	uint64_t q_span = 0;
 	{
@@ -478,9 +505,10 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		}
 		rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span, s.twobit);
 		if (!rc) rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span, s.twobit);
+		if (!s.ev_up) CU(h, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming | (wait_blocking() ? cudaEventBlockingSync : 0)));
+		if (!rc) CU(h, cudaEventRecord(s.ev_up, st));      // behind the sequence copies: what must complete before the caller's buffers are free
 		if (s.gate) {
-			if (!s.ev_up) CU(h, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
-			if (!rc) { CU(h, cudaEventRecord(s.ev_up, st)); s.gate->last = s.ev_up; }
+			if (!rc) s.gate->last = s.ev_up;
 			s.gate->pass(s.gate_turn);
 		}
 		if (rc) return rc;
@@ -491,13 +519,20 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	if ((rc = choose_variants(b, s, in, q_span))) return rc;
 	if (jump && (rc = build_jump_mask(b, s, in))) return rc;
 	mark("alphabet+jmask");
+	// a UNIFORM shard (every pair of the same shape, all on K1) needs no per-pair work on the host at all: see below
+	const uint32_t l1u = in->q_len[s.p0], l2u = in->t_len[s.p0];
+	bool uniform = b->mode <= AT_FIT && l1u <= 32u * MAXR && !getenv("AT_NO_UNIFORM_PLAN");
+	for (uint32_t k = 1; k < n && uniform; ++k) uniform = in->q_len[s.p0 + k] == l1u && in->t_len[s.p0 + k] == l2u;
 	// per-pair class, result arrays
-	s.h_rclass.resize(n);
 	s.cells = 0;
-	for (uint32_t k = 0; k < n; ++k) {
-		const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
-		s.h_rclass[k] = (uint8_t)rclass_of(l1);
-		s.cells += (uint64_t)l1 * l2;
+	if (uniform) s.cells = (uint64_t)n * l1u * l2u;
+	else {
+		s.h_rclass.resize(n);
+		for (uint32_t k = 0; k < n; ++k) {
+			const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
+			s.h_rclass[k] = (uint8_t)rclass_of(l1);
+			s.cells += (uint64_t)l1 * l2;
+		}
 	}
 	CU(h, s.d_score.alloc(n)); CU(h, s.d_end_i.alloc(n)); CU(h, s.d_end_j.alloc(n)); CU(h, s.d_end_state.alloc(n));
 	CU(h, s.d_beg_i.alloc(n)); CU(h, s.d_beg_j.alloc(n)); CU(h, s.d_n_ops.alloc(n + 1)); CU(h, s.d_n_cols.alloc(n + 1));
@@ -518,7 +553,8 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		const uint32_t l1 = in->q_len[s.p0 + k], l2 = in->t_len[s.p0 + k];
 		return b->traceback ? ptr_words_of(b->mode, jump, l1, l2) + 64ull * rclass_of(l1) : 0;   // + rounding slack of the packed layout
 	};
-	for (uint32_t k = 0; k < n; ++k) need_words += pair_words(k);
+	if (uniform) need_words = (uint64_t)n * pair_words(0);
+	else for (uint32_t k = 0; k < n; ++k) need_words += pair_words(k);
 	size_t free_b = 0, total_b = 0;
 	const bool owned = need_words <= s.d_ptr.n && !getenv("AT_PTR_BUDGET_MB");
 	if (!owned && need_words) {
@@ -546,6 +582,49 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		return p16_mode && l1 <= 32u * MAXR && l2 <= 60000u && 8 * (int64_t)(l1 + l2 + 42) * maxabs < (p16_local ? 32000 : 24000);      // + 40: K1 also computes up to 34 columns past l2
 	};
 	release_chunks(s);      // a pipeline worker reuses its shard (and the shard-level buffers) for every sub-slice
+	// ---- uniform shard: every pair has the same shape and runs on K1 in one chunk -> the plan is closed form ----
+	{
+		if (uniform && need_words && need_words > budget_words) {      // several chunks: the general plan (it needs the per-pair classes)
+			uniform = false;
+			s.h_rclass.assign(n, (uint8_t)rclass_of(l1u));
+		}
+		if (uniform) {
+			const bool packed = p16_ok(l1u, l2u) && n >= 2;
+			const uint32_t R = rclass_of(l1u);
+			const uint32_t tl = (l2u + 31u) | (packed ? 3u : (jump ? 31u : 7u));
+			const uint64_t words_per_job = !b->traceback ? 0 : packed ? (uint64_t)((tl >> 2) + 1) * R * 32 : ptr_words_of(b->mode, jump, l1u, l2u);
+			const uint64_t n_jobs = packed ? (n + 1) / 2 : n;
+			s.chunks.emplace_back();
+			Chunk &c = s.chunks.back();
+			c.k0 = 0; c.k1 = n;
+			c.ptr_words = words_per_job * n_jobs;
+			c.scratch_words = b->traceback ? (uint64_t)n * (l1u + l2u) : 0;
+			c.launches.emplace_back();
+			Launch &l = c.launches.back();
+			l.kind = packed ? LK_PACKED : LK_INT32; l.r = (int)R; l.cells = (uint64_t)n * l1u * l2u; l.n_planned = n_jobs;
+			CU(h, l.d_jobs.alloc(n_jobs)); CU(h, c.d_ptr_off.alloc(n)); CU(h, c.d_bnd_off.alloc(n)); CU(h, s.d_rclass.alloc(n));
+			if (b->traceback) { CU(h, c.d_ops_off.alloc(n + 1)); CU(h, c.d_cols_off.alloc(n + 1)); CU(h, c.d_scratch_off.alloc(n)); }
+			// on this stream, behind the uploads; the host does not wait for it (it may sit behind another sub-slice's fill)
+			at_plan_uniform<<<(n + 255) / 256, 256, 0, st>>>(n, packed ? 1 : 0, R, words_per_job, (uint64_t)l1u + l2u, l.d_jobs.p, c.d_ptr_off.p, c.d_bnd_off.p,
+			                                                 b->traceback ? c.d_scratch_off.p : nullptr, s.d_rclass.p);
+			CU(h, cudaGetLastError());
+			h->launches++;
+			s.ptr_bytes = c.ptr_words * 4;
+			CU(h, s.d_bnd.alloc(64)); CU(h, s.d_prog.alloc(1)); CU(h, s.d_chain.alloc(4ull * n + 4));
+			if (c.scratch_words && s.d_scratch.alloc(c.scratch_words) != cudaSuccess) { set_err(h, "traceback scratch of %llu MB", (unsigned long long)(c.scratch_words >> 18)); return AT_E_NOMEM; }
+			if (c.ptr_words) {
+				cudaError_t e = s.d_ptr.alloc(c.ptr_words + (s.workspace && c.ptr_words > s.d_ptr.n ? c.ptr_words / 16 : 0));
+				if (e != cudaSuccess) { set_err(h, "pointer arena of %llu MB: %s", (unsigned long long)(c.ptr_words >> 18), cudaGetErrorString(e)); return AT_E_NOMEM; }
+			}
+			for (auto &e : s.ev) if (!e) CU(h, event_create_timed(&e));
+			for (auto &e : s.evk) if (!e) CU(h, event_create_timed(&e));
+			mark("uniform plan");
+			CU(h, cudaEventSynchronize(s.ev_up));      // the caller's buffers have been read; the plan kernel may still be queued
+			mark("sync");
+			if (trace_setup) fprintf(stderr, "[at setup] pairs %u:%s\n", n, tl_.c_str());
+			return AT_OK;
+		}
+	}
 	uint64_t max_chunk_words = 0, max_scratch_words = 0;
 	{
 		Chunk cur; cur.k0 = 0;
@@ -704,21 +783,24 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 		cudaError_t e = s.d_ptr.alloc(max_chunk_words + (s.workspace && max_chunk_words > s.d_ptr.n ? max_chunk_words / 16 : 0));
 		if (e != cudaSuccess) { set_err(h, "pointer arena of %llu MB: %s", (unsigned long long)(max_chunk_words >> 18), cudaGetErrorString(e)); return AT_E_NOMEM; }
 	}
-	for (auto &e : s.ev) if (!e) CU(h, cudaEventCreate(&e));
-	for (auto &e : s.evk) if (!e) CU(h, cudaEventCreate(&e));
+	for (auto &e : s.ev) if (!e) CU(h, event_create_timed(&e));
+	for (auto &e : s.evk) if (!e) CU(h, event_create_timed(&e));
 	mark("arena");
 	// the ONE synchronisation of the set-up: every upload has left the caller's buffers (they may be reused or freed once
 	// at_batch_create / the sub-slice's set-up returns) and the shard's own host vectors
-	CU(h, cudaStreamSynchronize(st));
+	CU(h, shard_sync(s));
 	mark("sync");
-	if (trace_setup) fprintf(stderr, "[at setup] pairs %u:%s\n", n, tl.c_str());
+	if (trace_setup) fprintf(stderr, "[at setup] pairs %u:%s\n", n, tl_.c_str());
 	return AT_OK;
 }
 
 // argument checks shared by at_batch_create and the pipelined at_batch_align; mirrors the reference's own failure modes
 // `prefix` (optional): receives the running cell counts, prefix[k] = sum of l1*l2 over pairs < k (n_pairs + 1 entries),
 // so that the one-shot path validates, counts and slices a million-pair batch in one pass
-static int validate_batch(at_handle *h, int mode, const at_params *p, const at_batch_input *in, std::vector<uint64_t> *prefix = nullptr)
+// `wave_tasks` (optional): number of K2 tasks -- (pair, stripe of 256 rows) -- the batch will run as, 0 for pairs that go to K1:
+// the one-shot path sizes its sub-slices so that each still fills the GPU several times over
+static int validate_batch(at_handle *h, int mode, const at_params *p, const at_batch_input *in, std::vector<uint64_t> *prefix = nullptr,
+                          uint64_t *wave_tasks = nullptr)
 {
 	if (mode < AT_GLOBAL || mode > AT_EDIT) { set_err(h, "bad mode %d", mode); return AT_E_ARG; }
 	if (!in->n_pairs || !in->q || !in->q_off || !in->q_len || !in->t || !in->t_off || !in->t_len) { set_err(h, "align: parameter error"); return AT_E_ARG; }
@@ -749,16 +831,18 @@ static int validate_batch(at_handle *h, int mode, const at_params *p, const at_b
 	// the running cell counts in a second pass once every range knows its base
 	const uint64_t n = in->n_pairs;
 	const size_t parts = n >= (1u << 17) ? 4 : 1;
-	std::vector<uint64_t> lo(parts + 1), sum(parts, 0), bad(parts, UINT64_MAX);
+	std::vector<uint64_t> lo(parts + 1), sum(parts, 0), bad(parts, UINT64_MAX), tasks(parts, 0);
+	const bool all_wave = mode >= AT_OVERLAP;
 	for (size_t r = 0; r <= parts; ++r) lo[r] = n * r / parts;
 	auto pass1 = [&](size_t r) {
-		uint64_t acc = 0;
+		uint64_t acc = 0, tk = 0;
 		for (uint64_t k = lo[r]; k < lo[r + 1]; ++k) {
 			const uint64_t l1 = in->q_len[k], l2 = in->t_len[k];
 			if (check(k, l1, l2, false)) { bad[r] = k; break; }
 			acc += l1 * l2;
+			if (all_wave || l1 > 32u * MAXR) tk += (l1 + 32u * MAXR - 1) / (32u * MAXR);
 		}
-		sum[r] = acc;
+		sum[r] = acc; tasks[r] = tk;
 	};
 	auto pass2 = [&](size_t r, uint64_t acc) {
 		for (uint64_t k = lo[r]; k < lo[r + 1]; ++k) { acc += (uint64_t)in->q_len[k] * in->t_len[k]; pre[k + 1] = acc; }
@@ -773,6 +857,7 @@ static int validate_batch(at_handle *h, int mode, const at_params *p, const at_b
 	each_range(pass1);
 	for (size_t r = 0; r < parts; ++r)
 		if (bad[r] != UINT64_MAX) return check(bad[r], in->q_len[bad[r]], in->t_len[bad[r]], true);   // the first failing pair, as a serial scan would report
+	if (wave_tasks) { *wave_tasks = 0; for (size_t r = 0; r < parts; ++r) *wave_tasks += tasks[r]; }
 	if (pre) {
 		std::vector<uint64_t> base(parts, 0);
 		for (size_t r = 1; r < parts; ++r) base[r] = base[r - 1] + sum[r - 1];
@@ -982,7 +1067,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
 				fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
 				fa.jmask = s.d_jmask.p; fa.symmap = s.d_symmap.p; fa.syms = s.syms;
-				fa.jobs = l.d_jobs.p; fa.n_jobs = (uint32_t)l.h_jobs.size();
+				fa.jobs = l.d_jobs.p; fa.n_jobs = (uint32_t)l.n_jobs();
 				fa.counter = s.d_counter.p + (l.kind == LK_PACKED ? 16 : 0) + l.r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
 				fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;
 				fa.m = b->prm.m; fa.u = b->prm.u; fa.o = b->prm.o; fa.e = b->prm.e; fa.jp = b->prm.j;
@@ -1060,7 +1145,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 			} else {
 				CU(h, cudaMemcpyAsync(&tot[0], c.d_ops_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 				CU(h, cudaMemcpyAsync(&tot[1], c.d_cols_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-				CU(h, cudaStreamSynchronize(st));
+				CU(h, shard_sync(s));
 				if (int rc = out_buffers(tot[0], tot[1])) return rc;
 			}
 			if (s.workspace && tb_overlap) at_traceback_emit<true><<<(int)(((uint64_t)nc * 32 + 127) / 128), 128, 0, st>>>(ta);
@@ -1075,12 +1160,12 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				(*fills_done)();
 				CU(h, cudaMemcpyAsync(&tot[0], c.d_ops_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 				CU(h, cudaMemcpyAsync(&tot[1], c.d_cols_off.p + nc, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-				CU(h, cudaStreamSynchronize(st));
+				CU(h, shard_sync(s));
 			}
 			c.tot_ops = tot[0]; c.tot_cols = tot[1];
 		}
 		CU(h, cudaEventRecord(e_tb, st));
-		CU(h, cudaStreamSynchronize(st));
+		CU(h, shard_sync(s));
 		CU(h, cudaEventElapsedTime(&ms, e_begin, e_fill)); s.fill_ms += ms;
 		CU(h, cudaEventElapsedTime(&ms, e_fill, e_tb)); s.tb_ms += ms;
 		if ((int)ci == dom_chunk) {
@@ -1156,13 +1241,13 @@ static int fetch_shard(at_batch *b, Shard &s, at_batch_output *out, bool want_ci
 				CU(h, cudaMemcpyAsync(out->aln2 + base_cols, c.aln2, c.tot_cols, cudaMemcpyDeviceToHost, st));
 			}
 		}
-		CU(h, cudaStreamSynchronize(st));
+		CU(h, shard_sync(s));
 		// chunk-local offsets -> global
 		if (want_cig && base_ops) for (uint32_t k = 0; k < nc; ++k) out->cigar_off[ob + c.k0 + k] += base_ops;
 		if (want_aln && base_cols) for (uint32_t k = 0; k < nc; ++k) out->aln_off[ob + c.k0 + k] += base_cols;
 		base_ops += c.tot_ops; base_cols += c.tot_cols;
 	}
-	CU(h, cudaStreamSynchronize(st));
+	CU(h, shard_sync(s));
 	return AT_OK;
 }
 
@@ -1200,6 +1285,20 @@ extern "C" void *at_host_alloc(size_t bytes)
 }
 
 extern "C" void at_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int at_host_register(void *p, size_t bytes)
+{
+	if (!p || !bytes) return AT_E_ARG;
+	if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return AT_E_CUDA; }
+	return AT_OK;
+}
+
+extern "C" int at_host_unregister(void *p)
+{
+	if (!p) return AT_E_ARG;
+	if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return AT_E_CUDA; }
+	return AT_OK;
+}
 
 extern "C" int64_t at_pack_2bit(const char *seq, uint64_t n, uint8_t *dst)
 {

@@ -10,6 +10,7 @@ gather of the per-rank result arrays (`gloo` on CPU hosts, `nccl`/`gloo` on GPU 
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import numpy as np
@@ -86,7 +87,7 @@ class HostGather:
     concatenates in pair order (one memcpy per rank).  torch.distributed only carries the segment names (and the
     caller's barrier); `tag` keeps the segment names of concurrent gathers apart."""
 
-    def __init__(self, dist, rank, world, n_pairs, cigar_cap_per_rank, tag):
+    def __init__(self, dist, rank, world, n_pairs, cigar_cap_per_rank, tag, pin=False):
         from multiprocessing import shared_memory
         self.rank, self.world, self.n = rank, world, n_pairs
         self.cap = int(cigar_cap_per_rank)
@@ -95,6 +96,7 @@ class HostGather:
         names = [None]
         self.shm = {}
         if rank == 0:
+            tag = "".join(ch for ch in str(tag) if ch.isalnum())[:24]
             names = [{k: f"atb2_{tag}_{os.getpid()}_{k}" for k in self.sizes}]
             for k, sz in self.sizes.items():
                 self.shm[k] = shared_memory.SharedMemory(name=names[0][k], create=True, size=max(sz, 8))
@@ -108,6 +110,16 @@ class HostGather:
                     resource_tracker.unregister(self.shm[k]._name, "shared_memory")
                 except Exception:
                     pass
+        # page-lock the segments in THIS process (every rank's device copies land in them directly); best effort
+        self.registered = []
+        if pin:
+            from . import load_library
+            lib = load_library()
+            for k in self.sizes:
+                buf = (C.c_char * self.shm[k].size).from_buffer(self.shm[k].buf)
+                addr = C.addressof(buf)
+                if lib.at_host_register(addr, self.shm[k].size) == 0:
+                    self.registered.append((addr, buf))
         self.arr = {k: np.ndarray((self.sizes[k] // (8 if k in ("cigar_off", "nops") else 4),),
                                   dtype=np.uint64 if k in ("cigar_off", "nops") else (np.int32 if k == "score" else np.uint32),
                                   buffer=self.shm[k].buf) for k in self.sizes}
@@ -138,6 +150,12 @@ class HostGather:
 
     def close(self):
         self.arr = None
+        if self.registered:
+            from . import load_library
+            lib = load_library()
+            for addr, buf in self.registered:
+                lib.at_host_unregister(addr)
+            self.registered = []
         for s in self.shm.values():
             try:
                 s.close()

@@ -325,7 +325,7 @@ def sharded_leg(al, A, dist, w, name, flags, rank, world, steps, barrier, expect
         dist.all_gather_object(caps, cap)
         cap = max(caps)
     from aligntools.c_b200.sharding import HostGather
-    hg = HostGather(dist, rank, world, n, cap, name)
+    hg = HostGather(dist, rank, world, n, cap, name, pin=True)
     keep = []
     arrs = {}
     enc = A.SEQ_BYTES
@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 / C5 lines")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded (strong-scaling) legs")
-    ap.add_argument("--c3-pairs", type=int, default=1024)
+    ap.add_argument("--c3-pairs", type=int, default=2048)
     ap.add_argument("--c4-pairs", type=int, default=256)
     ap.add_argument("--c5-pairs", type=int, default=8, help="C5 pairs per GPU (BASELINE: 64 pairs over 8 GPUs)")
     ap.add_argument("--cfg-steps", type=int, default=3)

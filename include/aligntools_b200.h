@@ -207,6 +207,10 @@ int  at_plan_slices(const uint32_t *q_len, const uint32_t *t_len, uint64_t n_pai
  * fails.  Pure convenience over cudaHostAlloc / cudaFreeHost, so that a C host needs no CUDA headers. */
 void *at_host_alloc(size_t bytes);
 void  at_host_free(void *p);
+/* Page-lock memory the caller already owns (e.g. a shared-memory segment several ranks write their slices into);
+ * 0 on success.  Undo with at_host_unregister before the memory is released. */
+int   at_host_register(void *p, size_t bytes);
+int   at_host_unregister(void *p);
 
 /* Helpers: 2-bit packing (returns number of bytes written = (n+3)/4, or <0 when a symbol
  * is not one of ACGT/acgt... only upper-case ACGT are accepted: the reference compares

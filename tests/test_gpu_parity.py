@@ -291,6 +291,7 @@ def test_pipelined_one_shot_equals_three_call_path(A, aligner, monkeypatch, mode
     b.free()
     monkeypatch.setenv("AT_PIPE_MIN_CELLS", "1")
     monkeypatch.setenv("AT_PIPE_SLICE_CELLS", "3000000")        # about 10 sub-slices
+    monkeypatch.setenv("AT_PIPE_MIN_TASKS", "1")                # (K2 workloads are otherwise cut only into GPU-filling sub-slices)
     res = aligner.align_arrays(md, opt, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites=sites, site_off=site_off, out_flags=flags)
     assert res.timing.launches > ref.n // 100
     assert np.array_equal(res.score, ref.score)

@@ -335,3 +335,22 @@ def test_batch_fit_junction_lists(built, oracle_mod, tmp_path):
     _write_pairs(bad, pairs[:2] + [(pairs[2][0], pairs[2][1], None)] + pairs[3:5])
     pr = subprocess.run([CLI, "batch", "fit", "-s", str(bad)], capture_output=True)
     assert pr.returncode == 255 and pr.stderr == b"FATAL ERROR: fail to read junction sites\n"
+
+
+@pytest.mark.gpu
+def test_reference_main_with_five_call_sites_bound_to_the_library(built, oracle_mod, fasta_dir):
+    """INTEGRATION.md 1 made literal: oracle/_ref/alignTools_dropin is the reference's OWN main.c / alignment.h /
+    kstring.c (compiled by oracle/Makefile from a scratch copy) in which only the five call sites (:345, :509, :736, :885,
+    :1000) call the at_* shims, linked against libaligntools_b200.so.  Every golden command must come out byte for byte."""
+    exe = os.path.join(os.path.dirname(oracle_mod.REF_CLI), "alignTools_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/alignTools_dropin not built (needs /root/reference at build time)")
+    n = 0
+    for v in load_cli()["vectors"]:
+        args = [a.replace("$T", fasta_dir) for a in v["argv"]]
+        pr = subprocess.run([exe] + args, capture_output=True)
+        assert pr.returncode == v["rc"], (v["id"], pr.returncode, pr.stderr[-300:])
+        assert hashlib.md5(pr.stdout).hexdigest() == v["stdout_md5"], (v["id"], pr.stdout[:120])
+        assert pr.stderr == v["stderr"].replace("$BIN", exe).replace("$T", fasta_dir).encode(), (v["id"], pr.stderr[-300:])
+        n += 1
+    assert n >= 35
