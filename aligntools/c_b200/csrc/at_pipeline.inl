@@ -138,9 +138,11 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 			if (rc) { std::lock_guard<std::mutex> lk(mu); failed = rc; cv.notify_all(); break; }
 		}
 	};
+	// never more workers than sub-slices: a device's single sub-slice must always land in worker 0's workspace, which
+	// holds the arena from the previous call (another worker's would be cold: 100 ms to allocate a 50 GB arena)
 	std::vector<std::thread> th;
 	for (size_t d = 0; d < nd; ++d)
-		for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, d, w);
+		for (int w = 0; w < n_workers && (size_t)w < per_dev[d].size(); ++w) th.emplace_back(worker, d, w);
 	for (auto &t : th) t.join();
 	if (failed.load()) return failed.load();
 	uint64_t all_ops = 0, all_cols = 0;

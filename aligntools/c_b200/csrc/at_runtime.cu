@@ -226,19 +226,13 @@ struct Shard {
 	int rc = AT_OK;
 };
 
-// How host threads wait for the device.  Spinning (the device's yield flag) has the lowest latency and is right when every
-// process has cores to spare; on a box where several ranks share few cores (one process per GPU, three pipeline workers
-// each) spinning waiters take the cores the workers need, so there the waits sleep on events created with
-// cudaEventBlockingSync.  AT_SYNC=block|spin overrides; default: block when LOCAL_WORLD_SIZE ranks leave < 6 cores each.
+// How host threads wait for the device.  Default: spin with yields (the device's cudaDeviceScheduleYield flag) -- the lowest
+// latency, and measured best even with 8 ranks x 3 pipeline workers on 32 cores (e2e C2 at N = 8: 37.0 ms spinning,
+// 38.8 ms sleeping; profiles/bench_r02_n8*.json).  AT_SYNC=block makes the waits sleep on events created with
+// cudaEventBlockingSync instead, for hosts where the cores are needed elsewhere.
 static bool wait_blocking()
 {
-	static const bool v = [] {
-		if (const char *e = getenv("AT_SYNC")) return e[0] == 'b' || e[0] == 'B';
-		const char *lw = getenv("LOCAL_WORLD_SIZE");
-		const unsigned ranks = lw ? (unsigned)std::max(1, atoi(lw)) : 1u;
-		const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
-		return cores / ranks < 6;
-	}();
+	static const bool v = [] { const char *e = getenv("AT_SYNC"); return e && (e[0] == 'b' || e[0] == 'B'); }();
 	return v;
 }
 static cudaError_t event_create_timed(cudaEvent_t *e) { return cudaEventCreateWithFlags(e, wait_blocking() ? cudaEventBlockingSync : cudaEventDefault); }
