@@ -41,14 +41,20 @@ def port_columns(ref, n):
     return lens, ref.ops[idx]
 
 
-def check(al, w, threads, with_cols=True):
+def check(al, w, threads, with_cols=True, twobit=False):
     mode = w["mode"]
     prm = w["params"]
     n = len(w["q_len"])
     opt = A.Opt(**prm)
     flags = 0 if mode == "edit" else A.OUT_CIGAR
-    b = al.batch(mode, opt, w["q"], w["q_off"], w["q_len"], w["t"], w["t_off"], w["t_len"],
-                 sites=w["sites"], site_off=w["site_off"], out_flags=flags)
+    if twobit:      # the layout bench.py's e2e leg hands over: 2-bit codes, records on 16-byte boundaries
+        q2, qo2, _ = A.pack_2bit(w["q"], w["q_off"], w["q_len"], align=16)
+        t2, to2, _ = A.pack_2bit(w["t"], w["t_off"], w["t_len"], align=16)
+        b = al.batch(mode, opt, q2, qo2, w["q_len"], t2, to2, w["t_len"], sites=w["sites"], site_off=w["site_off"],
+                     out_flags=flags, encoding=A.SEQ_2BIT)
+    else:
+        b = al.batch(mode, opt, w["q"], w["q_off"], w["q_len"], w["t"], w["t_off"], w["t_len"],
+                     sites=w["sites"], site_off=w["site_off"], out_flags=flags)
     tm = b.run()
     res = b.fetch()
     b.free()
@@ -115,6 +121,7 @@ def main():
     ap.add_argument("--slice", type=int, default=1 << 17)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--max-seconds", type=float, default=900.0, help="stop starting new C2 slices after this long")
+    ap.add_argument("--twobit", action="store_true", help="hand every other C2 slice over as 2-bit records (the HBM-resident packed path)")
     ap.add_argument("--c3", type=int, default=8)
     ap.add_argument("--c4", type=int, default=6)
     ap.add_argument("--c5", type=int, default=2)
@@ -133,8 +140,9 @@ def main():
         sl = dict(w)
         for k in ("q_off", "q_len", "t_off", "t_len"):
             sl[k] = np.ascontiguousarray(w[k][lo:hi])
-        r = check(al, sl, args.threads)
+        r = check(al, sl, args.threads, twobit=args.twobit and (lo // args.slice) % 2 == 1)   # odd slices 2-bit, even slices bytes
         r["first_pair"] = lo
+        r["twobit"] = bool(args.twobit and (lo // args.slice) % 2 == 1)
         doc["c2"]["slices"].append(r)
         for k, v in r.items():
             if k.endswith("mismatch") or k in ("pairs", "cells", "alignment_columns"):
