@@ -30,17 +30,25 @@
 namespace atb2 {
 
 #define AT_WAVE_WARPS 4
-constexpr int AT_WAVE_UNROLL_AFFINE = 2;     // steps per loop body (instruction-cache footprint, see the loops)
+#ifndef AT_WAVE_AFFINE_MINB
+#define AT_WAVE_AFFINE_MINB 4      // resident CTAs per SM the affine kernel is compiled for (128 registers)
+#endif
+#ifndef AT_WAVE_UNROLL_AFFINE_N
+#define AT_WAVE_UNROLL_AFFINE_N 2
+#endif
+constexpr int AT_WAVE_UNROLL_AFFINE = AT_WAVE_UNROLL_AFFINE_N;     // steps per loop body (instruction-cache footprint, see the loops)
 constexpr int AT_WAVE_UNROLL_OVERLAP = 4, AT_WAVE_UNROLL_EDIT = 8;
 #define AT_PROG_DONE 0xffffffffu
 
-struct WaveTask { uint32_t pair, stripe; };
+// One unit of K2 work: stripe `stripe` of pair `pair`.  `prev` is the queue index of the same pair's stripe above it (its
+// own index for stripe 0): the affine kernel waits on that task's progress word.
+struct __align__(16) WaveTask { uint32_t pair, stripe, prev, reserved; };
 
 struct WaveArgs {
 	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
 	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
 	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
-	const WaveTask *tasks;   // pair-major, stripes ascending
+	const WaveTask *tasks;   // the queue: a pair's stripes in ascending order (the host interleaves the pairs, at_runtime.cu)
 	uint32_t        n_tasks;
 	uint32_t       *counter; // task queue head
 	uint32_t       *prog;    // [n_tasks] columns of the task's last row that are visible in its slab
@@ -158,7 +166,7 @@ __device__ __forceinline__ void wait_columns(const uint32_t *prog, uint32_t need
 // LDS from the boundary ring); it enters through a multiply-add with a 0/1 lane mask, not a branch.
 // Boundary element (int4 per column): x = M + o (tag 3), y = L (tag 3), z = H (tagged), w unused.
 template <int MODE, bool JUMP, bool PROF>
-__global__ void __launch_bounds__(32 * AT_WAVE_WARPS, 4) at_wave_affine(const WaveArgs a)
+__global__ void __launch_bounds__(32 * AT_WAVE_WARPS, AT_WAVE_AFFINE_MINB) at_wave_affine(const WaveArgs a)
 {
 	typedef Lanes<false> V;
 	constexpr int R = 8, RPP = 32 * R;
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, 4) at_wave_affine(const Wa
 		int4 *bnd_pair = (int4 *)a.bnd + a.bnd_off[p - a.pair_base];
 		int4 *bnd_out = bnd_pair + (size_t)(stripe & 1u) * slab;
 		const int4 *bnd_in = bnd_pair + (size_t)((stripe & 1u) ^ 1u) * slab;
-		const uint32_t *prog_in = a.prog + (stripe ? job - 1 : job);
+		const uint32_t *prog_in = a.prog + tk.prev;
 		uint32_t seen = 0;
 		const uint32_t row0 = stripe * RPP + lane * R;
 		const bool feed = lane == 0 && stripe > 0;                         // this lane reads the boundary ring
