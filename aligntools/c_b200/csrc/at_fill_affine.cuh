@@ -59,7 +59,8 @@ struct FillJob { uint32_t a, b; };     // pair indices; b == a for int32 lanes o
 struct FillArgs2 {
 	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
 	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
-	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
+	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden, one byte per target symbol
+	const uint64_t *j_off;   // [pair] offset of the pair's mask (byte-encoded targets: the same array as t_off)
 	const uint8_t  *symmap;  // PROF: byte -> code 0..3 of the shard's target alphabet (256 entries)
 	uint32_t        syms;    // PROF: the byte of code c in bits 8c..8c+7
 	const FillJob  *jobs;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(32 * AT_FILL_WARPS, (PACKED && R <= 5) ? 5 : (
 		const uint32_t l1A = a.q_len[pA], l1B = a.q_len[pB], l2 = a.t_len[pA];
 		const uint8_t *__restrict__ qA = a.q + a.q_off[pA], *__restrict__ qB = a.q + a.q_off[pB];
 		const uint8_t *__restrict__ tA = a.t + a.t_off[pA], *__restrict__ tB = a.t + a.t_off[pB];
-		const uint8_t *__restrict__ jm = JUMP ? a.jmask + a.t_off[pA] : nullptr;
+		const uint8_t *__restrict__ jm = JUMP ? a.jmask + a.j_off[pA] : nullptr;
 		uint32_t *__restrict__ ptr = a.ptr + a.ptr_off[pA - a.pair_base];
 		const uint32_t t_last = (l2 + 31u) | (JUMP ? 31u : (SPW - 1u));
 		const uint32_t G = t_last / SPW + 1;

@@ -210,7 +210,9 @@ struct Shard {
 	DevBuf<uint8_t> d_symmap; DevBuf<uint32_t> d_symset;
 	bool prof = false; uint32_t syms = 0;      // query-profile variant of K1: the targets use <= 4 distinct bytes
 	bool bits = false;                         // bit-parallel edit distance: `-u 1` and reads of <= 8 distinct bytes
-	bool twobit = false;                       // the sequences stay 2-bit packed in HBM (AT_SEQ_2BIT input consumed directly by K1 / K3)
+	bool twobit = false;                       // the sequences stay 2-bit packed in HBM (AT_SEQ_2BIT input consumed directly by K1 / K2 / K3)
+	std::vector<uint64_t> h_t_rel;             // twobit + jump: device offsets of the packed targets (the jump masks copy their alignment)
+	DevBuf<uint64_t> d_j_off;                  // twobit + jump: per-pair offsets into d_jmask (byte-encoded targets use d_t_off)
 	BufCache cache;                            // released device blocks, reused by this shard's next allocations
 	struct UploadGate *gate = nullptr; uint64_t gate_turn = 0;   // pipelined path: sub-slices upload their sequences one at a time, in pair order
 	bool workspace = false;                    // pipeline workspace: reused for many sub-slices, buffers get head-room
@@ -285,7 +287,7 @@ __global__ void at_unpack_2bit(const uint8_t *src, const uint64_t *src_off, cons
 // offsets -- and the kernels read the codes directly; otherwise 2-bit input is expanded to bytes on the device.
 static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t *src, const uint64_t *off,
                        const uint32_t *len, DevBuf<uint8_t> &d_bytes, DevBuf<uint8_t> &d_packed, DevBuf<uint64_t> &d_off,
-                       DevBuf<uint32_t> &d_len, uint64_t *span_bytes, bool resident)
+                       DevBuf<uint32_t> &d_len, uint64_t *span_bytes, bool resident, std::vector<uint64_t> *keep_rel = nullptr)
 {
 	const uint32_t n = s.n;
 	cudaStream_t st = s.stream;
@@ -332,6 +334,7 @@ static int upload_side(at_handle *h, Shard &s, uint32_t encoding, const uint8_t 
 		*span_bytes = tot;
 	} else {
 		CU(h, cudaMemcpyAsync(d_off.p, rel.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		if (keep_rel) keep_rel->swap(rel);      // (the copy above has staged the pageable vector already)
 	}
 	// No synchronisation here: `rel` / `unp` / `stage` are pageable, so the runtime has staged them by the time
 	// cudaMemcpyAsync returns; the caller's (possibly pinned) sequence buffers stay valid until setup_shard's one
@@ -353,7 +356,7 @@ static void free_shard(Shard &s)
 {
 	if (s.dev) { cudaSetDevice(s.dev->id); tl_stream = s.stream; tl_big = s.dev->big.get(); }
 	tl_cache = &s.cache;
-	s.d_q.release(); s.d_t.release(); s.d_jmask.release(); s.d_rclass.release(); s.d_end_state.release();
+	s.d_q.release(); s.d_t.release(); s.d_jmask.release(); s.d_j_off.release(); s.d_rclass.release(); s.d_end_state.release();
 	s.d_q2.release(); s.d_t2.release();
 	s.d_q_off.release(); s.d_t_off.release(); s.d_site_off.release();
 	s.d_q_len.release(); s.d_t_len.release(); s.d_end_i.release(); s.d_end_j.release(); s.d_beg_i.release();
@@ -447,8 +450,24 @@ static int build_jump_mask(at_batch *b, Shard &s, const at_batch_input *in)
 	// params.jump == 2 (junction WHITELIST, the semantics of the comment at src/alignment.h:542-544): entering J is
 	// barred everywhere except on the listed indices -- the mask starts as all ones and the sites clear it
 	const bool whitelist = b->prm.jump == 2;
-	CU(h, s.d_jmask.alloc(s.d_t.n));
-	CU(h, cudaMemsetAsync(s.d_jmask.p, whitelist ? 1 : 0, s.d_t.n, st));
+	// byte-encoded targets: the mask is indexed like the targets (same offsets, same 16-byte alignment for the TMA tiles of
+	// K2).  2-bit resident targets: one mask byte per SYMBOL, each pair's mask placed so that it has the alignment K2's
+	// ring gives the expanded target -- 4 x (packed address mod 16) past a 16-byte boundary.
+	uint64_t mask_bytes = s.d_t.n;
+	if (s.twobit) {
+		std::vector<uint64_t> jo(n);
+		uint64_t cur = 0;
+		for (uint32_t k = 0; k < n; ++k) {
+			jo[k] = cur + 4 * (((uintptr_t)s.d_t.p + s.h_t_rel[k]) & 15u);
+			cur = (jo[k] + in->t_len[s.p0 + k] + 15u) & ~(uint64_t)15u;
+		}
+		mask_bytes = cur + AT_SEQ_SLACK;
+		CU(h, s.d_j_off.alloc(n));
+		CU(h, cudaMemcpyAsync(s.d_j_off.p, jo.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	}
+	const uint64_t *d_j_off = s.twobit ? s.d_j_off.p : s.d_t_off.p;
+	CU(h, s.d_jmask.alloc(mask_bytes));
+	CU(h, cudaMemsetAsync(s.d_jmask.p, whitelist ? 1 : 0, mask_bytes, st));
 	if (!in->sites || !in->site_off) return AT_OK;
 	const uint64_t lo = in->site_off[s.p0], hi = in->site_off[s.p1];
 	std::vector<uint64_t> so(n + 1);
@@ -456,7 +475,7 @@ static int build_jump_mask(at_batch *b, Shard &s, const at_batch_input *in)
 	CU(h, s.d_sites.alloc(hi - lo + 1)); CU(h, s.d_site_off.alloc(n + 1));
 	if (hi > lo) CU(h, cudaMemcpyAsync(s.d_sites.p, in->sites + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
 	CU(h, cudaMemcpyAsync(s.d_site_off.p, so.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-	at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, s.d_t_off.p, s.d_t_len.p, n, s.d_jmask.p, whitelist ? 0 : 1);
+	at_build_jmask<<<n, 64, 0, st>>>(s.d_sites.p, s.d_site_off.p, d_j_off, s.d_t_len.p, n, s.d_jmask.p, whitelist ? 0 : 1);
 	CU(h, cudaGetLastError());
 	h->launches++;
 	return AT_OK;
@@ -523,20 +542,18 @@ static int setup_shard(at_batch *b, Shard &s, const at_batch_input *in)
 	{
 		// a pipeline worker waits for the uploads of the sub-slices before its own: the first (small) sub-slice's
 		// sequences are not held up behind a later, larger one sharing the copy engine, and its fill starts early
-		// 2-bit input stays packed in HBM when every pair of the shard runs on K1's query-profile variant (affine mode
-		// without jump state, reads of at most 256 rows): the fill reads the codes with 128-bit / byte loads and the
-		// traceback decodes them; no expansion kernel, a quarter of the sequence bytes.  Anything else expands to bytes.
-		s.twobit = false;
-		if (in->encoding == AT_SEQ_2BIT && b->mode <= AT_FIT && !(b->mode == AT_FIT && b->prm.jump) && !getenv("AT_NO_PROFILE") && !getenv("AT_NO_2BIT_RESIDENT")) {
-			s.twobit = true;
-			for (uint32_t k = 0; k < n && s.twobit; ++k) s.twobit = in->q_len[s.p0 + k] <= 32u * MAXR;
-		}
+		// 2-bit input stays packed in HBM: K1 reads the codes with 128-bit / byte loads (the code IS the query-profile
+		// index), K2 stages 64-byte tiles by TMA and expands them into its shared-memory ring once per 256 columns, the
+		// traceback decodes them; no expansion kernel, a quarter of the sequence bytes in HBM and over PCIe.  (The alphabet
+		// is ACGT by construction, so the query-profile variants always apply; AT_NO_PROFILE falls back to expanding.)
+		s.twobit = in->encoding == AT_SEQ_2BIT && !getenv("AT_NO_PROFILE") && !getenv("AT_NO_2BIT_RESIDENT");
 		if (s.gate) {
 			s.gate->wait_for(s.gate_turn);
 			if (s.gate->last) CU(h, cudaStreamWaitEvent(st, s.gate->last, 0));      // copy engine: earlier sub-slices first
 		}
 		rc = upload_side(h, s, in->encoding, in->q, in->q_off, in->q_len, s.d_q, s.d_q2, s.d_q_off, s.d_q_len, &q_span, s.twobit);
-		if (!rc) rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span, s.twobit);
+		if (!rc) rc = upload_side(h, s, in->encoding, in->t, in->t_off, in->t_len, s.d_t, s.d_t2, s.d_t_off, s.d_t_len, &s.t_span, s.twobit,
+		                          s.twobit && b->mode == AT_FIT && b->prm.jump ? &s.h_t_rel : nullptr);
 		if (!s.ev_up) CU(h, cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming | (wait_blocking() ? cudaEventBlockingSync : 0)));
 		if (!rc) CU(h, cudaEventRecord(s.ev_up, st));      // behind the sequence copies: what must complete before the caller's buffers are free
 		if (s.gate) {
@@ -1085,7 +1102,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				wa.symmap = s.d_symmap.p; wa.syms = s.syms;
 				wa.q = s.d_q.p; wa.q_off = s.d_q_off.p; wa.q_len = s.d_q_len.p;
 				wa.t = s.d_t.p; wa.t_off = s.d_t_off.p; wa.t_len = s.d_t_len.p;
-				wa.jmask = s.d_jmask.p; wa.tasks = l.d_tasks.p; wa.n_tasks = (uint32_t)l.h_tasks.size();
+				wa.jmask = s.d_jmask.p; wa.j_off = s.twobit && jump ? s.d_j_off.p : s.d_t_off.p; wa.twobit = s.twobit ? 1 : 0; wa.tasks = l.d_tasks.p; wa.n_tasks = (uint32_t)l.h_tasks.size();
 				wa.counter = s.d_counter.p + (l.kind == LK_BITS ? 48 : 32) + l.r; wa.prog = s.d_prog.p + l.prog_base;
 				wa.ptr = s.d_ptr.p; wa.ptr_off = c.d_ptr_off.p; wa.pair_base = c.k0;
 				wa.bnd = s.d_bnd.p; wa.bnd_off = c.d_bnd_off.p; wa.chain = s.d_chain.p;
@@ -1099,7 +1116,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				FillArgs2 fa;
 				fa.q = s.d_q.p; fa.q_off = s.d_q_off.p; fa.q_len = s.d_q_len.p;
 				fa.t = s.d_t.p; fa.t_off = s.d_t_off.p; fa.t_len = s.d_t_len.p;
-				fa.jmask = s.d_jmask.p; fa.symmap = s.d_symmap.p; fa.syms = s.syms;
+				fa.jmask = s.d_jmask.p; fa.j_off = s.twobit && jump ? s.d_j_off.p : s.d_t_off.p; fa.symmap = s.d_symmap.p; fa.syms = s.syms;
 				fa.jobs = l.d_jobs.p; fa.n_jobs = (uint32_t)l.n_jobs();
 				fa.counter = s.d_counter.p + (l.kind == LK_PACKED ? 16 : 0) + l.r; fa.ptr = s.d_ptr.p; fa.ptr_off = c.d_ptr_off.p; fa.pair_base = c.k0;
 				fa.score = s.d_score.p; fa.end_i = s.d_end_i.p; fa.end_j = s.d_end_j.p; fa.end_state = s.d_end_state.p;

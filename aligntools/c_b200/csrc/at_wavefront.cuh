@@ -47,7 +47,8 @@ struct __align__(16) WaveTask { uint32_t pair, stripe, prev, reserved; };
 struct WaveArgs {
 	const uint8_t  *q;       const uint64_t *q_off;  const uint32_t *q_len;
 	const uint8_t  *t;       const uint64_t *t_off;  const uint32_t *t_len;
-	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden; indexed like t
+	const uint8_t  *jmask;   // fit+jump: 1 where entering J is forbidden, one byte per target symbol
+	const uint64_t *j_off;   // [pair] offset of the pair's mask (byte-encoded targets: the same array as t_off)
 	const WaveTask *tasks;   // the queue: a pair's stripes in ascending order (the host interleaves the pairs, at_runtime.cu)
 	uint32_t        n_tasks;
 	uint32_t       *counter; // task queue head
@@ -63,6 +64,7 @@ struct WaveArgs {
 	                         // at_wave_linear<.., PROF>: byte -> code 0..3 of the shard's TARGET alphabet
 	uint32_t        syms;    // PROF: the byte of code c in bits 8c..8c+7
 	uint32_t        k_and, k_or;   // affine kernel: cell_k_and / cell_k_or (at_cell.cuh: constants that must stay in registers)
+	int             twobit;  // q / t hold 2-bit codes (AT_SEQ_2BIT resident: four symbols per byte, A C G T = 0..3, byte-aligned records)
 };
 
 // ---- TMA (bulk async copy) + mbarrier + release/acquire helpers ----
@@ -124,22 +126,50 @@ __device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
 // Per-warp target ring: two 256-byte slots per plane, slot c & 1 holds tile c of the target
 // (bytes base + 256*c .. +255 where base is the pair's target address rounded DOWN to 16 bytes,
 // as cp.async.bulk wants; `sh` = the rounding, so target index x lives at ring[(x + sh) & 511]).
+// 2-bit resident targets: a tile is 64 packed bytes; TMA stages them in pk[] and the warp expands them into the
+// byte ring once per 256 columns (ring_expand), so the column loops read the same bytes either way.  `sh` is then
+// four times the rounding of the packed address.
 template <bool JUMP> struct __align__(16) WaveRing {
 	uint8_t  tring[512];
 	uint8_t  jring[JUMP ? 512 : 16];
+	uint8_t  pk[2][64];
 	uint64_t bar[2];
 };
 
 template <bool JUMP>
-__device__ __forceinline__ void ring_issue(WaveRing<JUMP> &rg, const uint8_t *tbase16, const uint8_t *jbase16, uint32_t c, int lane)
+__device__ __forceinline__ void ring_issue(WaveRing<JUMP> &rg, const uint8_t *tbase16, const uint8_t *jbase16, uint32_t c, int lane, bool twobit)
 {
 	if (lane == 0) {
 		fence_proxy_async_smem();      // the slot's previous contents were read through the generic proxy
 		uint64_t *bar = &rg.bar[c & 1];
-		mbar_expect_tx(bar, JUMP ? 512u : 256u);
-		tma_load_1d(rg.tring + 256u * (c & 1), tbase16 + 256ull * c, 256u, bar);
+		mbar_expect_tx(bar, (twobit ? 64u : 256u) + (JUMP ? 256u : 0u));
+		if (twobit) tma_load_1d(rg.pk[c & 1], tbase16 + 64ull * c, 64u, bar);
+		else tma_load_1d(rg.tring + 256u * (c & 1), tbase16 + 256ull * c, 256u, bar);
 		if (JUMP) tma_load_1d(rg.jring + 256u * (c & 1), jbase16 + 256ull * c, 256u, bar);
 	}
+}
+
+__device__ __forceinline__ uint32_t sym_of_code(uint32_t code) { return (0x54474341u >> (8u * code)) & 255u; }      // "ACGT"[code]
+
+// tile c has landed in pk[c & 1]: 64 packed bytes -> 256 symbols of the byte ring (two packed bytes per lane)
+template <bool JUMP>
+__device__ __forceinline__ void ring_expand(WaveRing<JUMP> &rg, uint32_t c, int lane)
+{
+	const uint32_t two = ((const uint16_t *)rg.pk[c & 1])[lane];
+	uint32_t lo = 0, hi = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		lo |= sym_of_code((two >> (2 * k)) & 3u) << (8 * k);
+		hi |= sym_of_code((two >> (8 + 2 * k)) & 3u) << (8 * k);
+	}
+	((uint2 *)(rg.tring + 256u * (c & 1)))[lane] = make_uint2(lo, hi);
+	__syncwarp();
+}
+
+// symbol ri of a read: a byte, or "ACGT"[its 2-bit code]
+__device__ __forceinline__ uint32_t read_sym(const uint8_t *__restrict__ q, uint32_t ri, bool twobit)
+{
+	return twobit ? sym_of_code(((uint32_t)q[ri >> 2] >> (2u * (ri & 3u))) & 3u) : (uint32_t)q[ri];
 }
 
 // Wait until the predecessor task has published column `need` (warp-uniform; `seen` caches the last value read).
@@ -202,10 +232,13 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, AT_WAVE_AFFINE_MINB) at_wa
 		const uint32_t p = tk.pair, stripe = tk.stripe;
 		const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
 		const uint8_t *__restrict__ q = a.q + a.q_off[p];
+		const bool twobit = a.twobit != 0;
 		const uint8_t *tbase = a.t + a.t_off[p];
-		const uint32_t sh = (uint32_t)((uintptr_t)tbase & 15u);
-		const uint8_t *tbase16 = tbase - sh;
-		const uint8_t *jbase16 = JUMP ? a.jmask + a.t_off[p] - sh : nullptr;     // jmask and t share their layout (and alignment)
+		const uint32_t sh16 = (uint32_t)((uintptr_t)tbase & 15u);
+		const uint8_t *tbase16 = tbase - sh16;
+		const uint32_t sh = twobit ? 4u * sh16 : sh16;                        // ring position of target index 0
+		const uint32_t tile_wait = twobit ? 192u : 224u;                      // step (mod 256) at which the next tile must have landed: lane 0 is up to sh + 1 columns ahead of the step counter
+		const uint8_t *jbase16 = JUMP ? a.jmask + a.j_off[p] - sh : nullptr;     // the host lays the masks out with the targets' ring alignment
 		const uint32_t n_tiles = (l2 + sh + 255u) >> 8;
 		uint32_t *__restrict__ ptr = a.ptr + a.ptr_off[p - a.pair_base];
 		const uint32_t t_ptr_last = (l2 + 31u) | (JUMP ? 31u : 7u);       // pointer-block geometry shared with K1 / K3
@@ -225,8 +258,8 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, AT_WAVE_AFFINE_MINB) at_wa
 		const bool park = lane == 31 && !last_stripe;                      // this lane parks its last row for the next stripe
 
 		__syncwarp();
-		if (n_tiles > 0) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 0, lane);
-		if (n_tiles > 1) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 1, lane);
+		if (n_tiles > 0) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 0, lane, twobit);
+		if (n_tiles > 1) ring_issue<JUMP>(sm.rg, tbase16, jbase16, 1, lane, twobit);
 
 		RowState<false, JUMP> st[R];
 		int crow[R];
@@ -235,9 +268,9 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, AT_WAVE_AFFINE_MINB) at_wa
 		for (int r = 0; r < R; ++r) {
 			const uint32_t ri = row0 + r;
 			const int i = (int)ri + 1;
-			ac[r] = ri < l1 ? ((uint32_t)q[ri] << 16) : 0x4u;
+			ac[r] = ri < l1 ? (read_sym(q, ri, twobit) << 16) : 0x4u;
 			if (PROF) {
-				const uint32_t qa = ri < l1 ? (uint32_t)q[ri] : 0x100u;
+				const uint32_t qa = ri < l1 ? read_sym(q, ri, twobit) : 0x100u;
 #pragma unroll
 				for (int c = 0; c < 4; ++c) sm.prof[c][lane][r] = 8 * (qa == ((a.syms >> (8 * c)) & 255u) ? m : u);
 			}
@@ -285,6 +318,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, AT_WAVE_AFFINE_MINB) at_wa
 			if ((uint32_t)lane <= l2) pre = __ldcg(bnd_in + lane);
 		}
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
+		if (twobit) ring_expand(sm.rg, 0, lane);
 
 		// `cap`: std::true_type in the pair's last stripe -- only there can a lane hold the row whose cells the
 		// end-cell search looks at; the other stripes run a body without it
@@ -363,11 +397,11 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, AT_WAVE_AFFINE_MINB) at_wa
 			if ((tb & 255u) == 32u && tb > 32u) {     // tile tb/256 - 1 is dead: refill its slot two tiles ahead
 				const uint32_t c = (tb >> 8) + 1u;
 				__syncwarp();
-				if (c < n_tiles) ring_issue<JUMP>(sm.rg, tbase16, jbase16, c, lane);
+				if (c < n_tiles) ring_issue<JUMP>(sm.rg, tbase16, jbase16, c, lane, twobit);
 			}
-			if ((tb & 255u) == 224u) {                // the first lane enters tile tb/256 + 1 within the next 32 steps
+			if ((tb & 255u) == tile_wait) {           // the first lane enters tile tb/256 + 1 within the next 32 steps (2-bit: 64, sh <= 60)
 				const uint32_t c = (tb >> 8) + 1u;
-				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
+				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); if (twobit) ring_expand(sm.rg, c, lane); }
 			}
 			// two steps per loop body: 8 rows x 2 steps already is ~400 instructions; a fully unrolled pointer
 			// word (8 steps) overflows the instruction cache (ncu: stall_no_instruction was the top stall)
@@ -495,9 +529,12 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		const uint32_t p = tk.pair, stripe = tk.stripe;
 		const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
 		const uint8_t *__restrict__ q = a.q + a.q_off[p];
+		const bool twobit = a.twobit != 0;
 		const uint8_t *tbase = a.t + a.t_off[p];
-		const uint32_t sh = (uint32_t)((uintptr_t)tbase & 15u);
-		const uint8_t *tbase16 = tbase - sh;
+		const uint32_t sh16 = (uint32_t)((uintptr_t)tbase & 15u);
+		const uint8_t *tbase16 = tbase - sh16;
+		const uint32_t sh = twobit ? 4u * sh16 : sh16;                        // ring position of target index 0
+		const uint32_t tile_wait = twobit ? 192u : 224u;                      // step (mod 256) at which the next tile must have landed: lane 0 is up to sh + 1 columns ahead of the step counter
 		const uint32_t n_tiles = (l2 + sh + 255u) >> 8;
 		uint32_t *__restrict__ ptr = OV ? a.ptr + a.ptr_off[p - a.pair_base] : nullptr;
 		const uint32_t G = (((l2 + 31u) | 15u) >> 4) + 1;                 // pointer-block geometry shared with K3
@@ -517,8 +554,8 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		const bool park = lane == 31 && !last_stripe;                     // this lane parks its last row for the next stripe
 
 		__syncwarp();
-		if (n_tiles > 0) ring_issue<false>(sm.rg, tbase16, nullptr, 0, lane);
-		if (n_tiles > 1) ring_issue<false>(sm.rg, tbase16, nullptr, 1, lane);
+		if (n_tiles > 0) ring_issue<false>(sm.rg, tbase16, nullptr, 0, lane, twobit);
+		if (n_tiles > 1) ring_issue<false>(sm.rg, tbase16, nullptr, 1, lane, twobit);
 
 		// carried value: overlap a = 4*M + 4*o (LinRow keeps a + 2), edit M.  Column 0: M[i][0] = 0 (:938) | i (:301)
 		uint32_t ac[R];
@@ -527,11 +564,11 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 #pragma unroll
 		for (int r = 0; r < R; ++r) {
 			const uint32_t ri = row0 + r;
-			ac[r] = ri < l1 ? ((uint32_t)q[ri] << 16) : 0x4u;
+			ac[r] = ri < l1 ? (read_sym(q, ri, twobit) << 16) : 0x4u;
 			Vl[r] = (int)ri + 1;
 			stl[r].a2 = gap + 2; stl[r].x = 0;
 			if (PROF) {
-				const uint32_t qa = ri < l1 ? (uint32_t)q[ri] : 0x100u;
+				const uint32_t qa = ri < l1 ? read_sym(q, ri, twobit) : 0x100u;
 #pragma unroll
 				for (int c = 0; c < 4; ++c) sm.prof[c][lane][r] = pw_match + (qa == ((a.syms >> (8 * c)) & 255u) ? 0 : (int)pen * nsg);
 			}
@@ -559,6 +596,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 			if ((uint32_t)lane <= l2) pre = ld_relaxed_u64(bnd_in + lane);
 		}
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
+		if (twobit) ring_expand(sm.rg, 0, lane);
 
 		// `cap`: std::true_type in the pair's last stripe (only there can a lane hold the pair's last row)
 		auto step = [&](const uint32_t t, const bool checked, auto cap) {
@@ -630,11 +668,11 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 			if ((tb & 255u) == 32u && tb > 32u) {
 				const uint32_t c = (tb >> 8) + 1u;
 				__syncwarp();
-				if (c < n_tiles) ring_issue<false>(sm.rg, tbase16, nullptr, c, lane);
+				if (c < n_tiles) ring_issue<false>(sm.rg, tbase16, nullptr, c, lane, twobit);
 			}
-			if ((tb & 255u) == 224u) {
+			if ((tb & 255u) == tile_wait) {
 				const uint32_t c = (tb >> 8) + 1u;
-				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
+				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); if (twobit) ring_expand(sm.rg, c, lane); }
 			}
 			if (tb >= 32u && tb + 15u <= l2) {
 				if (last_stripe) {
@@ -711,9 +749,12 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 		const uint32_t p = tk.pair, stripe = tk.stripe;
 		const uint32_t l1 = a.q_len[p], l2 = a.t_len[p];
 		const uint8_t *__restrict__ q = a.q + a.q_off[p];
+		const bool twobit = a.twobit != 0;
 		const uint8_t *tbase = a.t + a.t_off[p];
-		const uint32_t sh = (uint32_t)((uintptr_t)tbase & 15u);
-		const uint8_t *tbase16 = tbase - sh;
+		const uint32_t sh16 = (uint32_t)((uintptr_t)tbase & 15u);
+		const uint8_t *tbase16 = tbase - sh16;
+		const uint32_t sh = twobit ? 4u * sh16 : sh16;                        // ring position of target index 0
+		const uint32_t tile_wait = twobit ? 192u : 224u;                      // step (mod 256) at which the next tile must have landed: lane 0 is up to sh + 1 columns ahead of the step counter
 		const uint32_t n_tiles = (l2 + sh + 255u) >> 8;
 		const uint32_t n_stripes = (l1 + RPP - 1) / RPP;
 		const bool last_stripe = stripe + 1 == n_stripes;
@@ -726,8 +767,8 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 		const uint32_t row0 = stripe * RPP + lane * 32u * R;
 
 		__syncwarp();
-		if (n_tiles > 0) ring_issue<false>(sm.rg, tbase16, nullptr, 0, lane);
-		if (n_tiles > 1) ring_issue<false>(sm.rg, tbase16, nullptr, 1, lane);
+		if (n_tiles > 0) ring_issue<false>(sm.rg, tbase16, nullptr, 0, lane, twobit);
+		if (n_tiles > 1) ring_issue<false>(sm.rg, tbase16, nullptr, 1, lane, twobit);
 
 		// match vectors of this lane's blocks: bit i of eq[c][lane][r] <=> read[row0 + 32 r + i] == symbol c
 #pragma unroll
@@ -737,7 +778,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 		for (int r = 0; r < R; ++r)
 			for (uint32_t i = 0; i < 32u; ++i) {
 				const uint32_t ri = row0 + 32u * r + i;
-				if (ri < l1) sm.eq[symmap_s[__ldg(q + ri)]][lane][r] |= 1u << i;
+				if (ri < l1) sm.eq[symmap_s[read_sym(q, ri, twobit)]][lane][r] |= 1u << i;
 			}
 		__syncwarp();
 
@@ -764,6 +805,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 			return in_bits;
 		};
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
+		if (twobit) ring_expand(sm.rg, 0, lane);
 		// Start lag: follow the predecessor four groups behind, so that the words requested one call ahead
 		// already carry its tag -- a follower on the predecessor's heels pays an L2 round trip per group.
 		if (stripe && lane == 0) {
@@ -866,11 +908,11 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_edit_bits(const Wa
 			if ((tb & 255u) == 96u && tb > 96u) {                          // lane 31 has left tile tb/256 - 1: refill its slot two tiles ahead
 				const uint32_t c = (tb >> 8) + 1u;
 				__syncwarp();
-				if (c < n_tiles) ring_issue<false>(sm.rg, tbase16, nullptr, c, lane);
+				if (c < n_tiles) ring_issue<false>(sm.rg, tbase16, nullptr, c, lane, twobit);
 			}
-			if ((tb & 255u) == 224u) {                                     // lane 0 enters tile tb/256 + 1 within the next 32 steps
+			if ((tb & 255u) == tile_wait) {                                // lane 0 enters tile tb/256 + 1 within the next 32 steps (2-bit: 64)
 				const uint32_t c = (tb >> 8) + 1u;
-				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); }
+				if (c < n_tiles) { mbar_wait(&sm.rg.bar[c & 1u], (ring_par >> (c & 1u)) & 1u); ring_par ^= 1u << (c & 1u); if (twobit) ring_expand(sm.rg, c, lane); }
 			}
 			if (tb >= 64u && tb + 14u <= l2) {
 				steps16(tb);

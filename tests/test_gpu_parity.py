@@ -342,12 +342,8 @@ def test_k1_query_profile_and_fallback_variants(A, aligner, oracle_mod, monkeypa
         check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites, site_off)
 
 
-@pytest.mark.parametrize("mode", ["global", "local", "fit", "fitjump", "overlap", "edit"])
-def test_k2_edge_shapes(A, aligner, oracle_mod, mode):
-    """Stripe-pipelined K2 at its corners: targets shorter than one 32-column hand-off block or one
-    TMA tile, reads of exactly one / one-plus-one stripes, single-column targets, long thin and
-    short wide matrices."""
-    rng = random.Random(31337)
+def _k2_edge_batch(mode, seed=31337):
+    rng = random.Random(seed)
     if mode.startswith("fit"):      # l1 <= l2, l2 >= 2
         shapes = [(257, 257), (257, 300), (513, 513), (1000, 1001), (256, 3000), (258, 259), (2049, 2100), (300, 4097)]
     else:
@@ -368,8 +364,68 @@ def test_k2_edge_shapes(A, aligner, oracle_mod, mode):
         for s2 in t:
             ss += sorted(rng.randrange(len(s2)) for _ in range(4)); so.append(len(ss))
         sites = np.array(ss + [0], dtype=np.int32); site_off = np.array(so, dtype=np.uint64)
-    md = "fit" if mode == "fitjump" else mode
-    check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites, site_off)
+    return ("fit" if mode == "fitjump" else mode), prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl, sites, site_off
+
+
+@pytest.mark.parametrize("mode", ["global", "local", "fit", "fitjump", "overlap", "edit"])
+def test_k2_edge_shapes(A, aligner, oracle_mod, mode):
+    """Stripe-pipelined K2 at its corners: targets shorter than one 32-column hand-off block or one
+    TMA tile, reads of exactly one / one-plus-one stripes, single-column targets, long thin and
+    short wide matrices."""
+    md, prm, qb, qo, ql, tb, to, tl, sites, site_off = _k2_edge_batch(mode)
+    check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo, ql, tb, to, tl, sites, site_off)
+
+
+@pytest.mark.parametrize("align", [1, 16])
+@pytest.mark.parametrize("mode", ["global", "local", "fit", "fitjump", "overlap", "edit", "edit-cells"])
+def test_k2_2bit_resident(A, aligner, oracle_mod, monkeypatch, mode, align):
+    """AT_SEQ_2BIT input stays 2-bit packed in HBM for the stripe-pipelined kernels too: TMA stages 64-byte tiles of
+    packed target, the warp expands them into its shared-memory ring, reads are decoded when a stripe starts, the jump
+    masks follow the expanded targets' ring alignment (records at arbitrary byte offsets: align=1)."""
+    if mode == "edit-cells":
+        monkeypatch.setenv("AT_NO_BITPAR", "1")      # the cell-by-cell single-plane kernel instead of the bit-parallel one
+    else:
+        monkeypatch.delenv("AT_NO_BITPAR", raising=False)
+    md, prm, qb, qo, ql, tb, to, tl, sites, site_off = _k2_edge_batch("edit" if mode == "edit-cells" else mode, seed=4242 + align)
+    q2, qo2, _ = A.pack_2bit(qb, qo, ql, align=align)
+    t2, to2, _ = A.pack_2bit(tb, to, tl, align=align)
+    tm = check_batch_vs_port(A, aligner, oracle_mod, md, prm, qb, qo, ql, tb, to, tl, sites, site_off,
+                             encoding=A.SEQ_2BIT, q_dev=q2, qo_dev=qo2, t_dev=t2, to_dev=to2)
+    assert tm.fill_kernel_flags & 4, "the batch was expanded to bytes instead of staying 2-bit resident"
+    if mode == "fitjump":      # the same lists as a whitelist
+        prm = dict(prm, jump=2)
+        opt = A.Opt(m=prm["m"], u=prm["u"], o=prm["o"], e=prm["e"], j=prm["j"], jump=True, whitelist=True)
+        p = oracle_mod.Params(prm["m"], prm["u"], prm["o"], prm["e"], prm["j"], 2)
+        ref = oracle_mod.port_batch("fit", p, qb, np.append(qo, 0).astype(np.uint64), ql, tb, np.append(to, 0).astype(np.uint64), tl,
+                                    sites, site_off, want_aln=True, want_ops=True, threads=8)
+        res = aligner.align_arrays("fit", opt, q2, qo2, ql, t2, to2, tl, sites=sites, site_off=site_off, encoding=A.SEQ_2BIT)
+        assert np.array_equal(res.score.astype(np.int64), ref.score)
+        for k in range(len(ql)):
+            assert res.cigar_string(k) == rle(ref.op(k)), k
+
+
+@pytest.mark.parametrize("mode", ["global", "local", "fit", "overlap", "edit"])
+def test_k2_2bit_ring_shift(A, aligner, oracle_mod, mode):
+    """2-bit targets whose packed records start 15 / 14 bytes past a 16-byte boundary: the expanded target sits up to 60
+    columns into K2's ring, so lane 0 enters the next 256-column tile up to 60 steps before the step counter does
+    (regression: the tile used to be awaited 32 steps ahead only)."""
+    rng = random.Random(77)
+    shapes = [(300, 60), (300, 700), (300, 300), (520, 1030), (300, 2000)]      # packed targets: 15, 175, 75, 258, 500 bytes
+    if mode == "fit":
+        shapes = [(30, 60)] + shapes[1:]
+    q, t = [], []
+    for l1, l2 in shapes:
+        base = bytes(rng.choice(b"ACGT") for _ in range(max(l1, l2)))
+        q.append(bytes(c if rng.random() > 0.1 else rng.choice(b"ACGT") for c in base[:l1]))
+        t.append(bytes(c if rng.random() > 0.1 else rng.choice(b"ACGT") for c in base[:l2]))
+    qb, qo, ql = pack_batch(q)
+    tb, to, tl = pack_batch(t)
+    q2, qo2, _ = A.pack_2bit(qb, qo[:-1].copy(), ql)
+    t2, to2, _ = A.pack_2bit(tb, to[:-1].copy(), tl)
+    assert [int(x) & 15 for x in to2[:3]] == [0, 15, 14]
+    prm = dict(m=1, u=-2, o=-3, e=-1, j=-5, jump=False)
+    check_batch_vs_port(A, aligner, oracle_mod, mode, prm, qb, qo[:-1].copy(), ql, tb, to[:-1].copy(), tl,
+                        encoding=A.SEQ_2BIT, q_dev=q2, qo_dev=qo2, t_dev=t2, to_dev=to2)
 
 
 @pytest.mark.parametrize("alphabet", [b"ACGT", b"A", b"ACGTNRYK", b"ACGTNRYKM", b"ACDEFGHIKLMNPQRSTVWY"])
