@@ -493,6 +493,9 @@ static int build_jump_mask(at_batch *b, Shard &s, const at_batch_input *in)
 // to fill the GPU and no longer.  A task's predecessor still precedes it in the queue, so a claimed task only ever
 // waits for a running one (deadlock freedom as before).  In: tasks collected pair by pair, stripes ascending.
 // AT_WAVE_ORDER=pair keeps the old order (A/B runs).
+// AT_WAVE_START_LAG (columns, default 0): a K2 stripe starts only once the stripe above it is this far ahead (A/B knob)
+static uint32_t wave_start_lag() { static const uint32_t v = [] { const char *e = getenv("AT_WAVE_START_LAG"); return e && *e ? (uint32_t)strtoul(e, nullptr, 10) : 0u; }(); return v; }
+
 static void order_wave_tasks(std::vector<WaveTask> &t)
 {
 	static const bool pair_major = [] { const char *e = getenv("AT_WAVE_ORDER"); return e && !strcmp(e, "pair"); }();
@@ -1102,7 +1105,7 @@ static int run_shard(at_batch *b, Shard &s, const std::function<void()> *fills_d
 				wa.symmap = s.d_symmap.p; wa.syms = s.syms;
 				wa.q = s.d_q.p; wa.q_off = s.d_q_off.p; wa.q_len = s.d_q_len.p;
 				wa.t = s.d_t.p; wa.t_off = s.d_t_off.p; wa.t_len = s.d_t_len.p;
-				wa.jmask = s.d_jmask.p; wa.j_off = s.twobit && jump ? s.d_j_off.p : s.d_t_off.p; wa.twobit = s.twobit ? 1 : 0; wa.tasks = l.d_tasks.p; wa.n_tasks = (uint32_t)l.h_tasks.size();
+				wa.jmask = s.d_jmask.p; wa.j_off = s.twobit && jump ? s.d_j_off.p : s.d_t_off.p; wa.twobit = s.twobit ? 1 : 0; wa.start_lag = wave_start_lag(); wa.tasks = l.d_tasks.p; wa.n_tasks = (uint32_t)l.h_tasks.size();
 				wa.counter = s.d_counter.p + (l.kind == LK_BITS ? 48 : 32) + l.r; wa.prog = s.d_prog.p + l.prog_base;
 				wa.ptr = s.d_ptr.p; wa.ptr_off = c.d_ptr_off.p; wa.pair_base = c.k0;
 				wa.bnd = s.d_bnd.p; wa.bnd_off = c.d_bnd_off.p; wa.chain = s.d_chain.p;

@@ -65,6 +65,7 @@ struct WaveArgs {
 	uint32_t        syms;    // PROF: the byte of code c in bits 8c..8c+7
 	uint32_t        k_and, k_or;   // affine kernel: cell_k_and / cell_k_or (at_cell.cuh: constants that must stay in registers)
 	int             twobit;  // q / t hold 2-bit codes (AT_SEQ_2BIT resident: four symbols per byte, A C G T = 0..3, byte-aligned records)
+	uint32_t        start_lag;   // a stripe starts once the stripe above it has published this many columns (0: as soon as it can)
 };
 
 // ---- TMA (bulk async copy) + mbarrier + release/acquire helpers ----
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS, AT_WAVE_AFFINE_MINB) at_wa
 		// first boundary block of the stripe above
 		int4 pre = make_int4(0, 0, 0, 0);
 		if (stripe) {
-			wait_columns(prog_in, min(l2, 31u), seen, lane);
+			wait_columns(prog_in, min(l2, max(31u, a.start_lag)), seen, lane);
 			if ((uint32_t)lane <= l2) pre = __ldcg(bnd_in + lane);
 		}
 		mbar_wait(&sm.rg.bar[0], ring_par & 1u); ring_par ^= 1u;
@@ -591,7 +592,7 @@ __global__ void __launch_bounds__(32 * AT_WAVE_WARPS) at_wave_linear(const WaveA
 		uint64_t pre = 0;
 		if (stripe) {
 			// start lag: three hand-off blocks behind the predecessor, so that blocks requested one block ahead are valid on arrival
-			if (lane == 0) { const uint32_t c = min(l2, 96u); while ((uint32_t)(ld_relaxed_u64(bnd_in + c) >> 32) != tag_in) __nanosleep(200); }
+			if (lane == 0) { const uint32_t c = min(l2, max(96u, a.start_lag)); while ((uint32_t)(ld_relaxed_u64(bnd_in + c) >> 32) != tag_in) __nanosleep(200); }
 			__syncwarp();
 			if ((uint32_t)lane <= l2) pre = ld_relaxed_u64(bnd_in + lane);
 		}
