@@ -168,13 +168,13 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 	pv.ptrJ = pv.ptr + (size_t)n_stripes * pv.G * pv.RPP;
 	RunWriter w;
 	w.dst = a.scratch + a.scratch_off[k]; w.n_ops = w.n_cols = w.run = 0; w.op = 0;
-	uint32_t i = a.end_i[p], j = a.end_j[p], state = a.end_state[p];
+	uint32_t i = a.end_i[p], j = a.end_j[p], state = a.end_state[p], tick = 3;
 	if (i) pv.seek(i);
 
 	if (a.mode == MODE_OVERLAP) {
 		while (j > 0) {                                   // :899
 			if (i == 0) break;                            // row 0 is -inf (:937): unreachable on a finite path
-			if (a.lookahead) pv.prefetch(i, j, 4);
+			if (a.lookahead && !(++tick & 3u)) pv.prefetch(i, j, 4);      // every fourth step: a sector holds eight rows of a lane block
 			const uint32_t c = pv.two(j);                 // bit 1: RIGHT beat both; bit 0: DIAGONAL beat LEFT
 			if (c & 2u)      { --i; pv.up(); w.col(CIG_I); }                  // RIGHT
 			else if (c & 1u) { --i; pv.up(); --j; w.col(CIG_M); }             // DIAGONAL
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 				state = pv.jbit(j) ? ST_JUMP : ST_MID; --j; w.col(CIG_N);
 				continue;
 			}
-			if (a.lookahead) pv.prefetch(i, j, pv.half ? 2 : 3);
+			if (a.lookahead && !(++tick & 3u)) pv.prefetch(i, j, pv.half ? 2 : 3);
 			const uint32_t nb = pv.nib(j);
 			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; pv.up(); w.col(CIG_I); }
 			else if (state == ST_MID) {

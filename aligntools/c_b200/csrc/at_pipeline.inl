@@ -36,12 +36,29 @@ static int align_pipelined(at_handle *h, int mode, const at_params *p, const at_
 		std::vector<uint64_t> cut;
 		cut_by_prefix(prefix, dcut[d], dcut[d + 1], units, cut);
 		const size_t max_group = (size_t)std::max<uint64_t>(1, env_u64("AT_PIPE_MAX_GROUP", 4));
-		for (size_t u0 = 0, step = 1; u0 < units; u0 += step, step = std::min<size_t>(2 * step, max_group)) {
-			const size_t u1 = std::min(units, u0 + step);
-			if (cut[u1] == cut[u0]) continue;
-			PipeSlice sl; sl.lo = cut[u0]; sl.hi = cut[u1]; sl.dev = d;
-			per_dev[d].push_back(slices.size());
-			slices.push_back(sl);
+		// ... and graduated again at the end (..., 4, 2, 1): what is left to do after the last fill -- the traceback of the
+		// last sub-slices and their D2H copies -- shrinks with them (C2: 1.2 ms after the last kernel with a full-size
+		// sub-slice second to last)
+		std::vector<size_t> tail;
+		for (size_t g = max_group / 2; g >= 1; g /= 2) tail.push_back(g);
+		size_t tail_units = 0;
+		for (size_t g : tail) tail_units += g;
+		if (units < 2 * tail_units + max_group || getenv("AT_PIPE_NO_RAMP_DOWN")) { tail.clear(); tail_units = 0; }
+		std::vector<size_t> groups;
+		for (size_t left = units - tail_units, step = 1; left > 0; step = std::min<size_t>(2 * step, max_group)) {
+			const size_t g = std::min(step, left);
+			groups.push_back(g); left -= g;
+		}
+		groups.insert(groups.end(), tail.begin(), tail.end());
+		size_t u0 = 0;
+		for (size_t g : groups) {
+			const size_t u1 = std::min(units, u0 + g);
+			if (cut[u1] != cut[u0]) {
+				PipeSlice sl; sl.lo = cut[u0]; sl.hi = cut[u1]; sl.dev = d;
+				per_dev[d].push_back(slices.size());
+				slices.push_back(sl);
+			}
+			u0 = u1;
 		}
 	}
 	// pipeline streams (created once per device)
