@@ -157,9 +157,12 @@ class HostGather:
                 lib.at_host_unregister(addr)
             self.registered = []
         for s in self.shm.values():
+            if self.rank == 0:      # unlink first: it works while views of the mapping are still alive, close() does not
+                try:
+                    s.unlink()
+                except Exception:
+                    pass
             try:
                 s.close()
-                if self.rank == 0:
-                    s.unlink()
             except Exception:
                 pass
