@@ -135,6 +135,10 @@ template <typename T> AT_HD T opaque(T v)
 // pipe to the compiler.  Measured (profiles/ab_fma_adds_r02.txt): the packed kernel is ALU-bound and gains 1.2 % (C2 fill
 // 31.11 -> 30.75 ms); the int32 kernels already lean on the FMA pipe and LOSE (C3 46.0 -> 54.2 ms, global 150 x 150
 // 1.35 -> 1.43 ms).  Hence: packed lanes only.
+// The jump-plane accumulator of the int32 kernels on the FMA pipe alone (A/B knob)
+#ifndef AT_CELL_FMA_XJ
+#define AT_CELL_FMA_XJ 0
+#endif
 #ifndef AT_CELL_FMA_ADDS
 #define AT_CELL_FMA_ADDS(PACKED) (PACKED)
 #endif
@@ -245,7 +249,12 @@ AT_HD typename Lanes<PACKED>::T cell_update(const CellConst<PACKED> &c, RowState
 	} else {
 		st.x = st.x * mul + (((uint32_t)(lk + mk) - (uint32_t)(lt + mt)) + (uint32_t)uk * 4u - (uint32_t)ut * 4u);
 	}
-	if (JUMP) st.xj = st.xj * mulj + ((uint32_t)jt - (uint32_t)jk);
+	if (JUMP) {
+		if (AT_CELL_FMA_XJ && !PACKED) {      // both terms as multiply-adds: the compiler's own choice is x + x on the FMA pipe and an IADD3 on the ALU pipe
+			const uint32_t t2 = fma_mad(st.xj, mulj, (uint32_t)jt);
+			st.xj = fma_mad((uint32_t)jk, c.neg1, t2);
+		} else st.xj = st.xj * mulj + ((uint32_t)jt - (uint32_t)jk);
+	}
 	const T d_next = st.h;
 	st.h = h; st.u = uk; st.mo = mo;
 	if (JUMP) st.j = jk;
