@@ -2,14 +2,16 @@
 // (included by at_kernels.cuh after the constants)
 //
 // A pair is cut into STRIPES of 32*R rows.  Every (pair, stripe) is a task; the persistent grid
-// claims tasks IN ORDER from an atomic queue, one warp per task, so the stripes of one pair run
-// concurrently on different warps / CTAs / SMs, each lagging its predecessor by three 32-column
-// blocks: the warps of a pair sit on an anti-diagonal of (stripe, column-block) tiles.  Inside a
+// claims tasks IN ORDER from an atomic queue, one warp per task.  The queue lists stripe after stripe
+// across the launch's pairs (order_wave_tasks, at_runtime.cu): stripes of one pair that happen to be
+// resident together run concurrently on different warps / CTAs / SMs, each at least two 32-column blocks
+// behind the one above; stripes claimed later find their predecessor finished.  Inside a
 // stripe the warp is the same systolic array as K1 (lane k owns R rows, column j = t - k).
 //
 //   * target tiles (and the jump blacklist) are staged by TMA: one elected lane issues
 //     cp.async.bulk global -> shared for the next 256-column tile into a two-slot ring and the
-//     warp waits on the slot's mbarrier just before the first lane enters the tile;
+//     warp waits on the slot's mbarrier just before the first lane enters the tile; 2-bit resident
+//     targets arrive as 64 packed bytes per tile and are expanded into the same byte ring;
 //   * the last row of a stripe (lane 31) is parked in a shared-memory stage, flushed 32 columns
 //     at a time with one coalesced store to the pair's boundary slab (L2 resident, two slabs
 //     alternating by stripe parity) and published with a release of the task's progress word;
@@ -19,8 +21,8 @@
 //     one dense 128*R-byte run per warp flush), so K3 walks both kernels' output.
 //
 // Deadlock freedom: tasks are claimed in queue order by warps that are all resident (grid =
-// occupancy x SMs), a warp only ever waits for the task claimed immediately before its own, and
-// stripe 0 of a pair waits for nothing.
+// occupancy x SMs), a warp only ever waits for a task that precedes its own in the queue (WaveTask::prev),
+// and stripe 0 of a pair waits for nothing.
 //
 // Reference recurrences: src/alignment.h:451-462 (global), :635-667 (fit), :825-841 (local),
 // :940-949 (overlap), :303-311 (edit); tie rules SURVEY.md A.0.

@@ -112,7 +112,9 @@ enum at_seq_encoding {
 	AT_SEQ_BYTES = 0,  /* one byte per symbol, any alphabet, compared verbatim            */
 	AT_SEQ_2BIT  = 1   /* four symbols per byte (A,C,G,T -> 0..3, symbol k of a record in
 	                      bits 2*(k&3) of byte k>>2); every record starts on a byte boundary
-	                      and *_off are BYTE offsets.  See at_pack_2bit().                 */
+	                      and *_off are BYTE offsets.  See at_pack_2bit().  The records stay
+	                      packed in device memory and every kernel reads the codes directly;
+	                      records on 16-byte boundaries are read with 128-bit loads.       */
 };
 
 typedef struct at_batch_input {
@@ -165,7 +167,7 @@ typedef struct at_timing {
 	uint64_t fill_kernel_cells; /* cells one such launch processes                                   */
 	uint32_t fill_kernel_kind;  /* which kernel that was: enum at_kernel_kind                            */
 	uint32_t fill_kernel_rows;  /* its rows per lane (AT_K_EDIT_BITS: 32-row blocks per lane)            */
-	uint32_t fill_kernel_flags; /* bit 0: query-profile variant, bit 1: jump state, bit 2: 2-bit targets */
+	uint32_t fill_kernel_flags; /* bit 0: query-profile variant, bit 1: jump state, bit 2: sequences 2-bit packed in HBM */
 	uint32_t reserved_;
 } at_timing;
 
