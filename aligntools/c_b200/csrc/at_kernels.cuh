@@ -38,6 +38,14 @@
 #include <stdint.h>
 #include "at_cell.cuh"      // Lanes<>, cell_update(), AT_NEG: the cell arithmetic shared by K1 and K2
 
+// traceback walker's look-ahead: how far ahead (steps) and how often (every PERIOD-th step, a power of two) it prefetches
+#ifndef AT_TB_PF_AHEAD
+#define AT_TB_PF_AHEAD 24
+#endif
+#ifndef AT_TB_PF_PERIOD
+#define AT_TB_PF_PERIOD 8
+#endif
+
 namespace atb2 {
 
 enum { MODE_GLOBAL = 0, MODE_LOCAL = 1, MODE_FIT = 2, MODE_OVERLAP = 3, MODE_EDIT = 4 };
@@ -105,7 +113,7 @@ struct PtrView {
 	// along the diagonal (rows and columns both move back) or along a row (gap / jump runs).  A thread-serial
 	// pointer chase otherwise pays a full HBM round trip per new sector.
 	__device__ __forceinline__ void prefetch(uint32_t i, uint32_t j, int sh) const {
-		constexpr uint32_t AHEAD = 24;
+		constexpr uint32_t AHEAD = AT_TB_PF_AHEAD;
 		if (i <= AHEAD + 1 || j <= AHEAD + 1 || rowA < AHEAD) return;
 		const uint32_t lane_then = lane - min(lane, (AHEAD + R - 1 - r) / R);               // rows per lane: R (approximate across a stripe edge)
 		const uint32_t *diag = ptr + (rowA - AHEAD) + (size_t)((j - AHEAD + lane_then) >> sh) * RPP;
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 	if (a.mode == MODE_OVERLAP) {
 		while (j > 0) {                                   // :899
 			if (i == 0) break;                            // row 0 is -inf (:937): unreachable on a finite path
-			if (a.lookahead && !(++tick & 3u)) pv.prefetch(i, j, 4);      // every fourth step: a sector holds eight rows of a lane block
+			if (a.lookahead && !(++tick & (AT_TB_PF_PERIOD - 1u))) pv.prefetch(i, j, 4);      // every AT_TB_PF_PERIOD-th step: a sector holds eight rows of a lane block
 			const uint32_t c = pv.two(j);                 // bit 1: RIGHT beat both; bit 0: DIAGONAL beat LEFT
 			if (c & 2u)      { --i; pv.up(); w.col(CIG_I); }                  // RIGHT
 			else if (c & 1u) { --i; pv.up(); --j; w.col(CIG_M); }             // DIAGONAL
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(128) at_traceback_walk(const TraceArgs a)
 				state = pv.jbit(j) ? ST_JUMP : ST_MID; --j; w.col(CIG_N);
 				continue;
 			}
-			if (a.lookahead && !(++tick & 3u)) pv.prefetch(i, j, pv.half ? 2 : 3);
+			if (a.lookahead && !(++tick & (AT_TB_PF_PERIOD - 1u))) pv.prefetch(i, j, pv.half ? 2 : 3);
 			const uint32_t nb = pv.nib(j);
 			if (state == ST_LOW)      { state = (nb & 4u) ? ST_MID : ST_LOW; --i; pv.up(); w.col(CIG_I); }
 			else if (state == ST_MID) {
